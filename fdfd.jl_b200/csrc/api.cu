@@ -1,0 +1,238 @@
+// api.cu -- C-ABI entry points built on the resident problem handle: driven TM/TE solve.
+#include "krylov.cuh"
+#include <chrono>
+#include <cmath>
+
+namespace {
+
+__global__ void k_scale_src(int64_t N, c128 k, const c128* __restrict__ src, c128* __restrict__ b) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x)
+    b[i] = k * src[i];
+}
+
+__global__ void k_fill_random(int64_t N, c128* __restrict__ x, uint64_t seed) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+    x[i] = c128((double)(z & 0xFFFFFFFF) / 4294967296.0 - 0.5, (double)(z >> 32) / 4294967296.0 - 0.5);
+  }
+}
+
+template <typename T> __global__ void k_cast_in(int64_t N, const c128* __restrict__ in, cplx<T>* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) out[i] = cplx<T>(in[i]);
+}
+template <typename T> __global__ void k_cast_out(int64_t N, const cplx<T>* __restrict__ in, c128* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) out[i] = c128(in[i]);
+}
+
+double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+int vec_blocks(fdfd_ctx* ctx, int64_t N) { return (int)std::min<int64_t>((N + 255) / 256, (int64_t)ctx->num_sms * 8); }
+
+}  // namespace
+
+int apply_num_blocks(int64_t nx, int64_t ny);
+
+static MGParams mg_params_from(const fdfd_solve_opts_t& o) {
+  MGParams m;
+  m.cycle = o.mg_cycle; m.wdepth = o.mg_wdepth; m.nu1 = std::max(1, o.mg_nu1); m.nu2 = std::max(0, o.mg_nu2);
+  m.coarse_sweeps = std::max(1, o.mg_coarse_sweeps);
+  m.beta = o.mg_beta; m.wjac = o.mg_wjac; m.wline = o.mg_wline;
+  return m;
+}
+
+extern "C" int fdfd_problem_create(fdfd_ctx* ctx, const fdfd_grid_t* g, int pol, int ordering, double omega,
+                                   const fdfd_c128* eps_r, const fdfd_solve_opts_t* opts, fdfd_problem** out) {
+  ARG_CHECK(ctx, ctx != nullptr, "ctx is NULL");
+  ARG_CHECK(ctx, out != nullptr, "out is NULL");
+  *out = nullptr;
+  FDFD_TRY(check_grid(ctx, g));
+  ARG_CHECK(ctx, pol == FDFD_TM || pol == FDFD_TE, "pol must be FDFD_TM or FDFD_TE");
+  ARG_CHECK(ctx, ordering == FDFD_ORDER_FB || ordering == FDFD_ORDER_BF, "bad ordering");
+  ARG_CHECK(ctx, eps_r != nullptr, "eps_r is NULL");
+  ARG_CHECK(ctx, omega > 0, "omega must be > 0");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  fdfd_problem* P = new fdfd_problem();
+  P->ctx = ctx;
+  if (opts) P->opts = *opts; else fdfd_default_opts(&P->opts);
+  ARG_CHECK(ctx, P->opts.solver == FDFD_SOLVER_BICGSTAB, "only FDFD_SOLVER_BICGSTAB is implemented in this build");
+  const double t0 = now_ms();
+  int st = P->op.build(ctx, *g, pol, ordering, omega, eps_r);
+  if (st != FDFD_OK) { delete P; return st; }
+  const int64_t N = g->Nx * g->Ny;
+  auto fail = [&](int code) { delete P; return code; };
+#define PALLOC(buf, n) do { if ((buf).alloc(n) != cudaSuccess) { fdfd_set_error(ctx, "out of device memory allocating %zu elements", (size_t)(n)); return fail(FDFD_ERR_ALLOC); } } while (0)
+  PALLOC(P->b, N); PALLOC(P->x, N); PALLOC(P->r, N); PALLOC(P->rhat, N); PALLOC(P->p, N); PALLOC(P->v, N); PALLOC(P->s, N); PALLOC(P->t, N);
+  if (P->opts.precond == FDFD_PRECOND_JACOBI) { PALLOC(P->ph, N); PALLOC(P->sh, N); }
+  P->nvec_blocks = vec_blocks(ctx, N);
+  const int nparts = std::max(P->nvec_blocks, apply_num_blocks(g->Nx, g->Ny));
+  PALLOC(P->partials, (size_t)nparts * 2);
+  PALLOC(P->scal, 1);
+  PALLOC(P->hist, (size_t)std::max(16, P->opts.maxit + 2));
+#undef PALLOC
+  if (cudaMallocHost((void**)&P->h_scal, sizeof(KScal)) != cudaSuccess) { fdfd_set_error(ctx, "cudaMallocHost failed"); return fail(FDFD_ERR_ALLOC); }
+  if (P->opts.precond == FDFD_PRECOND_MG) {
+    MGParams mp = mg_params_from(P->opts);
+    if (P->opts.mg_precision == FDFD_MG_F64) { P->mgd = new Multigrid<double>(); st = P->mgd->setup(ctx, P->op, mp); P->mgd->done = &P->scal.p->done; }
+    else { P->mgf = new Multigrid<float>(); st = P->mgf->setup(ctx, P->op, mp); P->mgf->done = &P->scal.p->done; }
+    if (st != FDFD_OK) return fail(st);
+  }
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { fdfd_set_error(ctx, "setup failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(FDFD_ERR_CUDA); }
+  P->setup_ms = now_ms() - t0;
+  *out = P;
+  return FDFD_OK;
+}
+
+extern "C" void fdfd_problem_destroy(fdfd_problem* p) {
+  if (!p) return;
+  cudaSetDevice(p->ctx->device);
+  cudaStreamSynchronize(p->ctx->stream);
+  delete p;
+}
+
+extern "C" int fdfd_problem_set_rhs(fdfd_problem* P, const fdfd_c128* b) {
+  if (!P) return FDFD_ERR_ARG;
+  ARG_CHECK(P->ctx, b != nullptr, "b is NULL");
+  const int64_t N = P->op.g.Nx * P->op.g.Ny;
+  FDFD_TRY(fdfd_copy_in(P->ctx, P->b.p, b, N * sizeof(c128)));
+  CUDA_TRY(P->ctx, cudaStreamSynchronize(P->ctx->stream));
+  P->have_rhs = true;
+  return FDFD_OK;
+}
+
+extern "C" int fdfd_problem_set_source(fdfd_problem* P, const fdfd_c128* src) {
+  if (!P) return FDFD_ERR_ARG;
+  fdfd_ctx* ctx = P->ctx;
+  ARG_CHECK(ctx, src != nullptr, "src is NULL");
+  const int64_t N = P->op.g.Nx * P->op.g.Ny;
+  // stage src in t (scratch), b = 1im*ω*src (driven.jl:36)
+  FDFD_TRY(fdfd_copy_in(ctx, P->t.p, src, N * sizeof(c128)));
+  k_scale_src<<<P->nvec_blocks, 256, 0, ctx->stream>>>(N, c128(0.0, P->op.omega), P->t.p, P->b.p); KLAUNCH(ctx);
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  P->have_rhs = true;
+  return FDFD_OK;
+}
+
+extern "C" int fdfd_problem_solve(fdfd_problem* P, fdfd_info_t* info) {
+  if (!P) return FDFD_ERR_ARG;
+  ARG_CHECK(P->ctx, P->have_rhs, "no right-hand side set");
+  fdfd_info_t local{};
+  if (!info) info = &local;
+  std::memset(info, 0, sizeof(*info));
+  CUDA_TRY(P->ctx, cudaSetDevice(P->ctx->device));
+  const double t0 = now_ms();
+  FDFD_TRY(problem_solve_bicgstab(P, info));
+  info->total_ms = now_ms() - t0;
+  if (info->flag != FDFD_OK) fdfd_set_error(P->ctx, "Krylov solver stopped with flag %d after %d iterations, relres %.3e", info->flag, info->iters, info->relres);
+  return FDFD_OK;  // convergence state is reported through info->flag; results are valid approximations
+}
+
+extern "C" int fdfd_problem_get_solution(fdfd_problem* P, fdfd_c128* x) {
+  if (!P) return FDFD_ERR_ARG;
+  ARG_CHECK(P->ctx, x != nullptr, "x is NULL");
+  const int64_t N = P->op.g.Nx * P->op.g.Ny;
+  FDFD_TRY(fdfd_copy_out(P->ctx, x, P->x.p, N * sizeof(c128)));
+  CUDA_TRY(P->ctx, cudaStreamSynchronize(P->ctx->stream));
+  return FDFD_OK;
+}
+
+extern "C" int fdfd_problem_get_fields(fdfd_problem* P, int forward_h, fdfd_c128* fields) {
+  if (!P) return FDFD_ERR_ARG;
+  fdfd_ctx* ctx = P->ctx;
+  ARG_CHECK(ctx, fields != nullptr, "fields is NULL");
+  const int64_t N = P->op.g.Nx * P->op.g.Ny;
+  DevBuf<c128> f3;
+  CUDA_TRY(ctx, f3.alloc(3 * N));
+  FDFD_TRY(launch_recover(ctx, P->op, P->x.p, forward_h, std::complex<double>(P->op.omega, 0.0), 0, f3.p));
+  FDFD_TRY(fdfd_copy_out(ctx, fields, f3.p, 3 * N * sizeof(c128)));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return FDFD_OK;
+}
+
+extern "C" int fdfd_problem_bench_apply(fdfd_problem* P, int nrep, double* ms_per_apply) {
+  if (!P) return FDFD_ERR_ARG;
+  fdfd_ctx* ctx = P->ctx;
+  ARG_CHECK(ctx, nrep > 0 && ms_per_apply, "bad arguments");
+  const int64_t N = P->op.g.Nx * P->op.g.Ny;
+  const bool te = P->op.pol == FDFD_TE;
+  k_fill_random<<<P->nvec_blocks, 256, 0, ctx->stream>>>(N, P->p.p, 1234); KLAUNCH(ctx);
+  DotSpec ds;
+  for (int w = 0; w < 3; ++w) FDFD_TRY(launch_apply(ctx, P->op.view(), te, P->p.p, false, P->v.p, ds));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(ctx, cudaEventCreate(&e0)); CUDA_TRY(ctx, cudaEventCreate(&e1));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
+  for (int i = 0; i < nrep; ++i) {
+    // ping-pong so consecutive launches do not hit identical cache state
+    FDFD_TRY(launch_apply(ctx, P->op.view(), te, (i & 1) ? P->v.p : P->p.p, false, (i & 1) ? P->p.p : P->v.p, ds));
+  }
+  CUDA_TRY(ctx, cudaEventRecord(e1, ctx->stream));
+  CUDA_TRY(ctx, cudaEventSynchronize(e1));
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *ms_per_apply = (double)ms / nrep;
+  return FDFD_OK;
+}
+
+extern "C" int fdfd_problem_precond(fdfd_problem* P, const fdfd_c128* in, fdfd_c128* out) {
+  if (!P) return FDFD_ERR_ARG;
+  fdfd_ctx* ctx = P->ctx;
+  ARG_CHECK(ctx, in && out, "NULL argument");
+  ARG_CHECK(ctx, P->mgf || P->mgd, "problem has no multigrid preconditioner");
+  const int64_t N = P->op.g.Nx * P->op.g.Ny;
+  FDFD_TRY(fdfd_copy_in(ctx, P->t.p, in, N * sizeof(c128)));
+  const int blocks = P->nvec_blocks;
+  if (P->mgf) {
+    const int* saved = P->mgf->done; P->mgf->done = nullptr;
+    k_cast_in<float><<<blocks, 256, 0, ctx->stream>>>(N, P->t.p, P->mgf->rhs()); KLAUNCH(ctx);
+    const c64* res = nullptr;
+    int st = P->mgf->apply(&res);
+    P->mgf->done = saved;
+    FDFD_TRY(st);
+    k_cast_out<float><<<blocks, 256, 0, ctx->stream>>>(N, res, P->t.p); KLAUNCH(ctx);
+  } else {
+    const int* saved = P->mgd->done; P->mgd->done = nullptr;
+    k_cast_in<double><<<blocks, 256, 0, ctx->stream>>>(N, P->t.p, P->mgd->rhs()); KLAUNCH(ctx);
+    const c128* res = nullptr;
+    int st = P->mgd->apply(&res);
+    P->mgd->done = saved;
+    FDFD_TRY(st);
+    k_cast_out<double><<<blocks, 256, 0, ctx->stream>>>(N, res, P->t.p); KLAUNCH(ctx);
+  }
+  CUDA_TRY(ctx, cudaGetLastError());
+  FDFD_TRY(fdfd_copy_out(ctx, out, P->t.p, N * sizeof(c128)));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return FDFD_OK;
+}
+
+// ---- solve(d::Device, pol) ------------------------------------------------------------------------------
+extern "C" int fdfd_solve_driven(fdfd_ctx* ctx, const fdfd_grid_t* g, int pol, int n_omega, const double* omega,
+                                 const fdfd_c128* eps_r, const fdfd_c128* src, int src_per_omega,
+                                 const fdfd_solve_opts_t* opts, fdfd_c128* fields, fdfd_info_t* info) {
+  ARG_CHECK(ctx, ctx != nullptr, "ctx is NULL");
+  FDFD_TRY(check_grid(ctx, g));
+  ARG_CHECK(ctx, n_omega >= 1 && omega, "need at least one frequency");
+  ARG_CHECK(ctx, eps_r && src && fields, "NULL argument");
+  const int64_t N = g->Nx * g->Ny;
+  int worst = FDFD_OK;
+  for (int i = 0; i < n_omega; ++i) {  // driven.jl:11 -- everything is rebuilt per ω (PML depends on ω)
+    const double t0 = now_ms();
+    fdfd_problem* P = nullptr;
+    FDFD_TRY(fdfd_problem_create(ctx, g, pol, FDFD_ORDER_FB, omega[i], eps_r, opts, &P));
+    int st = fdfd_problem_set_source(P, src + (src_per_omega ? (size_t)i * N : 0));
+    fdfd_info_t inf{};
+    if (st == FDFD_OK) st = fdfd_problem_solve(P, &inf);
+    // driven.jl:40-41 (TM, backward) / 50-51 (TE, backward)
+    if (st == FDFD_OK) st = fdfd_problem_get_fields(P, 0, fields + (size_t)i * 3 * N);
+    fdfd_problem_destroy(P);
+    if (st != FDFD_OK) return st;
+    inf.total_ms = now_ms() - t0;
+    if (info) info[i] = inf;
+    if (inf.flag != FDFD_OK) worst = inf.flag;
+  }
+  if (worst != FDFD_OK) { fdfd_set_error(ctx, "fdfd_solve_driven: at least one frequency did not converge (flag %d)", worst); return worst; }
+  return FDFD_OK;
+}

@@ -1,0 +1,47 @@
+// device_ops.cuh -- operator views shared by assembly, stencil, Krylov and multigrid code.
+#pragma once
+#include "common.cuh"
+
+// Every level of every operator on the path has this shape:
+//   (A u)[ix,iy] = W (u[ix-1]-u) + E (u[ix+1]-u) + S (u[iy-1]-u) + Nn (u[iy+1]-u) + m u        (periodic)
+//   TM: W=cxm[ix] E=cxp[ix] S=cym[iy] Nn=cyp[iy]  m=mass[ix,iy]
+//   TE: W=cxm[ix] gx[ix,iy]  E=cxp[ix] gx[ix+1,iy]  S=cym[iy] gy[ix,iy]  Nn=cyp[iy] gy[ix,iy+1]  m=mass_const
+template <typename T> struct OpView {
+  int64_t nx, ny;
+  const cplx<T>* cxm; const cplx<T>* cxp; const cplx<T>* cym; const cplx<T>* cyp;
+  const cplx<T>* mass;            // 2-D, TM
+  const cplx<T>* gx; const cplx<T>* gy;  // 2-D, TE
+  cplx<T> mass_const;
+};
+
+// fp64 fine-grid operator resident in HBM
+struct FineOp {
+  fdfd_grid_t g{};
+  int pol = FDFD_TM, ordering = FDFD_ORDER_FB;
+  double omega = 0;
+  DevBuf<c128> c1d;    // cxm | cxp | cym | cyp
+  DevBuf<c128> mass;   // TM: w^2 eps0 L0 eps_r
+  DevBuf<c128> gx, gy; // TE: 1 / grid_average(eps0 L0 eps_r, x|y)
+  DevBuf<c128> eps;    // eps_r as given (kept for multigrid setup)
+  c128 mass_const{0.0, 0.0};
+  Coef1D hc;           // host copy of the 1-D coefficients
+
+  int build(fdfd_ctx* ctx, const fdfd_grid_t& g, int pol, int ordering, double omega, const fdfd_c128* eps_r_any);
+  OpView<double> view() const {
+    OpView<double> v;
+    v.nx = g.Nx; v.ny = g.Ny;
+    v.cxm = c1d.p; v.cxp = c1d.p + g.Nx; v.cym = c1d.p + 2 * g.Nx; v.cyp = c1d.p + 2 * g.Nx + g.Ny;
+    v.mass = mass.p; v.gx = gx.p; v.gy = gy.p; v.mass_const = mass_const;
+    return v;
+  }
+};
+
+// ---- launch wrappers implemented in stencil.cu ------------------------------------------------
+// y = A x.  TI = element type of x (c128 or c64), y is c128.  Optional fused dots (deterministic two-stage):
+//   ndot = 0: none;  1: partial[0] = <d0, y>;  2: partial[0] = <y, d0>, partial[1] = <y, y>   (conjugate-linear in 1st arg)
+struct DotSpec { int ndot = 0; const c128* d0 = nullptr; c128* partials = nullptr; int* nblocks_out = nullptr; const int* done = nullptr; };
+int launch_apply(fdfd_ctx* ctx, const OpView<double>& op, bool te, const void* x, bool x_is_f32, c128* y, const DotSpec& ds);
+
+// H/E recovery written straight into the (Nx,Ny,3) output (K9).  mode: see stencil.cu
+int launch_recover(fdfd_ctx* ctx, const FineOp& op, const c128* u, int forward, std::complex<double> omega_field,
+                   int te_swap, c128* fields3);

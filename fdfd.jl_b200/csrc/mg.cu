@@ -1,0 +1,450 @@
+// mg.cu -- shifted-Laplacian geometric multigrid (see mg.cuh for the design).
+#include "mg.cuh"
+#include <cmath>
+
+namespace {
+
+constexpr int kMgThreads = 128;
+constexpr int kMgRows = 4;
+
+// coefficients of row (ix,iy): W,E,S,N couplings and the diagonal C = m - W - E - S - N
+template <typename T, bool TE>
+__device__ __forceinline__ void row_coefs(const OpView<T>& op, int64_t ix, int64_t iy, int64_t ixp, int64_t iyp,
+                                          cplx<T>& W, cplx<T>& E, cplx<T>& S, cplx<T>& Nn, cplx<T>& C) {
+  const int64_t nx = op.nx;
+  W = op.cxm[ix]; E = op.cxp[ix]; S = op.cym[iy]; Nn = op.cyp[iy];
+  cplx<T> m;
+  if (TE) {
+    const int64_t n = ix + nx * iy;
+    W = W * op.gx[n]; E = E * op.gx[ixp + nx * iy];
+    S = S * op.gy[n]; Nn = Nn * op.gy[ix + nx * iyp];
+    m = op.mass_const;
+  } else {
+    m = op.mass[ix + nx * iy];
+  }
+  C = m - W - E - S - Nn;
+}
+
+template <typename T, bool TE>
+__device__ __forceinline__ cplx<T> residual_at(const OpView<T>& op, const cplx<T>* __restrict__ u,
+                                               const cplx<T>* __restrict__ f, int64_t ix, int64_t iy, cplx<T>* Cout) {
+  const int64_t nx = op.nx, ny = op.ny;
+  const int64_t ixm = ix == 0 ? nx - 1 : ix - 1, ixp = ix + 1 == nx ? 0 : ix + 1;
+  const int64_t iym = iy == 0 ? ny - 1 : iy - 1, iyp = iy + 1 == ny ? 0 : iy + 1;
+  cplx<T> W, E, S, Nn, C;
+  row_coefs<T, TE>(op, ix, iy, ixp, iyp, W, E, S, Nn, C);
+  cplx<T> r = f[ix + nx * iy];
+  r -= C * u[ix + nx * iy];
+  r -= W * u[ixm + nx * iy]; r -= E * u[ixp + nx * iy];
+  r -= S * u[ix + nx * iym]; r -= Nn * u[ix + nx * iyp];
+  if (Cout) *Cout = C;
+  return r;
+}
+
+__device__ __forceinline__ bool in_strip(int64_t i, int64_t n, int np) { return i < np || i >= n - np; }
+__device__ __forceinline__ int64_t strip_line(int64_t i, int64_t n, int np) { return i < np ? i : i - (n - 2 * np); }
+__device__ __forceinline__ int64_t strip_index(int64_t c, int64_t n, int np) { return c < np ? c : c + (n - 2 * np); }
+
+// ---- level setup --------------------------------------------------------------------------
+// TM: mass = (1 - i beta) w^2 eps0 eps ;  TE: gx, gy = 1/grid_average(eps0 eps)
+template <typename T, bool TE>
+__global__ void k_level_setup(int64_t nx, int64_t ny, const c128* __restrict__ eps, double w2eps0, double beta, double eps0,
+                              cplx<T>* __restrict__ mass, cplx<T>* __restrict__ gx, cplx<T>* __restrict__ gy) {
+  const int64_t N = nx * ny;
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+    const c128 e = eps[n];
+    if (!TE) {
+      // (1 - i beta) * w^2 eps0 * e
+      mass[n] = cplx<T>(T(w2eps0 * (e.x + beta * e.y)), T(w2eps0 * (e.y - beta * e.x)));
+    } else {
+      const int64_t ix = n % nx, iy = n / nx;
+      const int64_t ixm = ix == 0 ? nx - 1 : ix - 1, iym = iy == 0 ? ny - 1 : iy - 1;
+      const c128 ew = eps[ixm + nx * iy], es = eps[ix + nx * iym];
+      const c128 ax = c128(eps0 * (e.x + ew.x) / 2, eps0 * (e.y + ew.y) / 2);
+      const c128 ay = c128(eps0 * (e.x + es.x) / 2, eps0 * (e.y + es.y) / 2);
+      gx[n] = cplx<T>(crecip(ax)); gy[n] = cplx<T>(crecip(ay));
+    }
+  }
+}
+
+// 1-D transfer weights of coarse point I (fine 2I): centre 1/2, left/right 1/4 when that odd fine point exists
+__device__ __forceinline__ void fw_weights(int64_t I, int64_t nf, int64_t nc, int64_t idx[3], double w[3]) {
+  const bool even = (nf % 2) == 0;
+  idx[1] = 2 * I; w[1] = 0.5;
+  if (I == 0) { idx[0] = nf - 1; w[0] = even ? 0.25 : 0.0; } else { idx[0] = 2 * I - 1; w[0] = 0.25; }
+  if (2 * I + 1 <= nf - 1) { idx[2] = 2 * I + 1; w[2] = 0.25; } else { idx[2] = 0; w[2] = 0.0; }
+  (void)nc;
+}
+
+// eps restriction: normalised full weighting (an average)
+__global__ void k_restrict_eps(int64_t nxf, int64_t nyf, int64_t nxc, int64_t nyc, const c128* __restrict__ ef,
+                               c128* __restrict__ ec) {
+  const int64_t Nc = nxc * nyc;
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < Nc; n += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t I = n % nxc, J = n / nxc;
+    int64_t xi[3], yi[3]; double wx[3], wy[3];
+    fw_weights(I, nxf, nxc, xi, wx); fw_weights(J, nyf, nyc, yi, wy);
+    double sr = 0, si = 0, sw = 0;
+    for (int b = 0; b < 3; ++b)
+      for (int a = 0; a < 3; ++a) {
+        const double w = wx[a] * wy[b];
+        if (w == 0.0) continue;
+        const c128 e = ef[xi[a] + nxf * yi[b]];
+        sr += w * e.x; si += w * e.y; sw += w;
+      }
+    ec[n] = c128(sr / sw, si / sw);
+  }
+}
+
+// ---- PCR setup: one CTA per line, fp64, global scratch (a,b,c ping-pong) -------------------------
+// mode 0: y-lines (column ix = strip_index(c)), a=S, c=N.  mode 1: x-lines (row iy), a=W, c=E.  Wrap couplings
+// are dropped (they link the two deepest PML cells and stay in the lagged part of the splitting).
+template <typename T, bool TE>
+__global__ void k_pcr_setup(OpView<T> op, int mode, int np, int K, c128* __restrict__ scratch, cplx<T>* __restrict__ mult) {
+  const int64_t nx = op.nx, ny = op.ny;
+  const int64_t n = mode == 0 ? ny : nx;
+  const int64_t c = blockIdx.x;
+  const int64_t fixed = strip_index(c, mode == 0 ? nx : ny, np);
+  c128* a0 = scratch + (size_t)c * 6 * n; c128* b0 = a0 + n; c128* c0 = b0 + n;
+  c128* a1 = c0 + n; c128* b1 = a1 + n; c128* c1 = b1 + n;
+  cplx<T>* alpha = mult + (size_t)c * (2 * K + 1) * n;
+  cplx<T>* gamma = alpha + (size_t)K * n;
+  cplx<T>* binv = gamma + (size_t)K * n;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const int64_t ix = mode == 0 ? fixed : i, iy = mode == 0 ? i : fixed;
+    const int64_t ixp = ix + 1 == nx ? 0 : ix + 1, iyp = iy + 1 == ny ? 0 : iy + 1;
+    cplx<T> W, E, S, Nn, C;
+    row_coefs<T, TE>(op, ix, iy, ixp, iyp, W, E, S, Nn, C);
+    c128 lo = mode == 0 ? c128(S) : c128(W), hi = mode == 0 ? c128(Nn) : c128(E);
+    if (i == 0) lo = c128(0.0, 0.0);
+    if (i == n - 1) hi = c128(0.0, 0.0);
+    a0[i] = lo; b0[i] = c128(C); c0[i] = hi;
+  }
+  __syncthreads();
+  for (int k = 0; k < K; ++k) {
+    const int64_t s = (int64_t)1 << k;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+      c128 al(0.0, 0.0), ga(0.0, 0.0);
+      c128 bn = b0[i], an(0.0, 0.0), cn(0.0, 0.0);
+      if (i >= s) { al = -cdiv(a0[i], b0[i - s]); bn += al * c0[i - s]; an = al * a0[i - s]; }
+      if (i + s < n) { ga = -cdiv(c0[i], b0[i + s]); bn += ga * a0[i + s]; cn = ga * c0[i + s]; }
+      a1[i] = an; b1[i] = bn; c1[i] = cn;
+      alpha[(size_t)k * n + i] = cplx<T>(al); gamma[(size_t)k * n + i] = cplx<T>(ga);
+    }
+    __syncthreads();
+    c128* t;
+    t = a0; a0 = a1; a1 = t; t = b0; b0 = b1; b1 = t; t = c0; c0 = c1; c1 = t;
+  }
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) binv[i] = cplx<T>(crecip(b0[i]));
+}
+
+// ---- smoother, phase 1: point Jacobi outside the strips + residual capture on the strip columns ----------
+template <typename T, bool TE, bool ZERO>
+__global__ void __launch_bounds__(kMgThreads)
+k_smooth_pt(OpView<T> op, const cplx<T>* __restrict__ u, const cplx<T>* __restrict__ f, cplx<T>* __restrict__ out,
+            cplx<T>* __restrict__ rxs, int npx, int npy, T wj, const int* __restrict__ done) {
+  if (done && *done) return;
+  const int64_t nx = op.nx, ny = op.ny;
+  const int64_t ix = blockIdx.x * (int64_t)kMgThreads + threadIdx.x;
+  if (ix >= nx) return;
+  const bool xs = in_strip(ix, nx, npx);
+#pragma unroll
+  for (int r = 0; r < kMgRows; ++r) {
+    const int64_t iy = blockIdx.y * (int64_t)kMgRows + r;
+    if (iy >= ny) break;
+    const int64_t n = ix + nx * iy;
+    const bool ys = in_strip(iy, ny, npy);
+    const cplx<T> u0 = ZERO ? cplx<T>(T(0), T(0)) : u[n];
+    if (ys && !xs) { out[n] = u0; continue; }
+    cplx<T> C, res;
+    if (ZERO) {
+      res = f[n];
+      if (!xs) {
+        const int64_t ixp = ix + 1 == nx ? 0 : ix + 1, iyp = iy + 1 == ny ? 0 : iy + 1;
+        cplx<T> W, E, S, Nn;
+        row_coefs<T, TE>(op, ix, iy, ixp, iyp, W, E, S, Nn, C);
+      }
+    } else {
+      res = residual_at<T, TE>(op, u, f, ix, iy, &C);
+    }
+    if (xs) { rxs[strip_line(ix, nx, npx) * ny + iy] = res; out[n] = u0; }
+    else out[n] = u0 + wj * cdiv(res, C);
+  }
+}
+
+// ---- smoother, phase 3: residual on the strip rows (after the y-line update) ---------------------------
+template <typename T, bool TE>
+__global__ void k_resid_rows(OpView<T> op, const cplx<T>* __restrict__ u, const cplx<T>* __restrict__ f,
+                             cplx<T>* __restrict__ rys, int npy, const int* __restrict__ done) {
+  if (done && *done) return;
+  const int64_t nx = op.nx, ny = op.ny;
+  const int64_t ix = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t c = blockIdx.y;
+  if (ix >= nx) return;
+  const int64_t iy = strip_index(c, ny, npy);
+  rys[c * nx + ix] = residual_at<T, TE>(op, u, f, ix, iy, nullptr);
+}
+
+// ---- line solves: PCR on the right-hand side with precomputed multipliers ------------------------------
+// one CTA per line; d ping-pongs in shared memory (or a global scratch when the line is too long)
+template <typename T>
+__global__ void k_lines(int64_t n, int K, const cplx<T>* __restrict__ mult, const cplx<T>* __restrict__ rbuf,
+                        cplx<T>* __restrict__ out, int mode, int64_t nx, int64_t ny, int np, T wl,
+                        cplx<T>* __restrict__ gscratch, const int* __restrict__ done) {
+  if (done && *done) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int64_t c = blockIdx.x;
+  cplx<T>* d0 = gscratch ? gscratch + (size_t)c * 2 * n : reinterpret_cast<cplx<T>*>(smem_raw);
+  cplx<T>* d1 = d0 + n;
+  const cplx<T>* alpha = mult + (size_t)c * (2 * K + 1) * n;
+  const cplx<T>* gamma = alpha + (size_t)K * n;
+  const cplx<T>* binv = gamma + (size_t)K * n;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) d0[i] = rbuf[c * n + i];
+  __syncthreads();
+  for (int k = 0; k < K; ++k) {
+    const int64_t s = (int64_t)1 << k;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+      cplx<T> v = d0[i];
+      if (i >= s) v += alpha[(size_t)k * n + i] * d0[i - s];
+      if (i + s < n) v += gamma[(size_t)k * n + i] * d0[i + s];
+      d1[i] = v;
+    }
+    __syncthreads();
+    cplx<T>* t = d0; d0 = d1; d1 = t;
+  }
+  const int64_t fixed = strip_index(c, mode == 0 ? nx : ny, np);
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const int64_t idx = mode == 0 ? fixed + nx * i : i + nx * fixed;
+    out[idx] += wl * (d0[i] * binv[i]);
+  }
+}
+
+// ---- residual + full-weighting restriction (coarse-point-centric) --------------------------------------
+template <typename T, bool TE>
+__global__ void k_resid_restrict(OpView<T> op, const cplx<T>* __restrict__ u, const cplx<T>* __restrict__ f,
+                                 int64_t nxc, int64_t nyc, cplx<T>* __restrict__ fc, const int* __restrict__ done) {
+  if (done && *done) return;
+  const int64_t I = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t J = blockIdx.y;
+  if (I >= nxc) return;
+  int64_t xi[3], yi[3]; double wx[3], wy[3];
+  fw_weights(I, op.nx, nxc, xi, wx); fw_weights(J, op.ny, nyc, yi, wy);
+  cplx<T> acc(T(0), T(0));
+#pragma unroll
+  for (int b = 0; b < 3; ++b)
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const T w = T(wx[a] * wy[b]);
+      if (w == T(0)) continue;
+      acc += w * residual_at<T, TE>(op, u, f, xi[a], yi[b], nullptr);
+    }
+  fc[I + nxc * J] = acc;
+}
+
+// ---- bilinear prolongation + correction ------------------------------------------------------------------
+template <typename T>
+__global__ void k_prolong_add(int64_t nx, int64_t ny, int64_t nxc, int64_t nyc, const cplx<T>* __restrict__ uc,
+                              cplx<T>* __restrict__ u, const int* __restrict__ done) {
+  if (done && *done) return;
+  const int64_t ix = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t iy = blockIdx.y;
+  if (ix >= nx) return;
+  const int64_t I0 = ix >> 1, J0 = iy >> 1;
+  const bool ox = ix & 1, oy = iy & 1;
+  const int64_t I1 = ox ? (I0 + 1 == nxc ? 0 : I0 + 1) : I0;
+  const int64_t J1 = oy ? (J0 + 1 == nyc ? 0 : J0 + 1) : J0;
+  cplx<T> v = uc[I0 + nxc * J0];
+  if (ox) v += uc[I1 + nxc * J0];
+  if (oy) {
+    cplx<T> w = uc[I0 + nxc * J1];
+    if (ox) w += uc[I1 + nxc * J1];
+    v += w;
+  }
+  const T sc = (ox ? T(0.5) : T(1)) * (oy ? T(0.5) : T(1));
+  u[ix + nx * iy] += sc * v;
+}
+
+}  // namespace
+
+// ==============================================================================================
+template <typename T> int Multigrid<T>::setup(fdfd_ctx* ctx_, const FineOp& op, const MGParams& prm_) {
+  ctx = ctx_; prm = prm_; te = op.pol == FDFD_TE;
+  const fdfd_grid_t& g = op.g;
+  const double eps0 = kEps0 * g.L0, mu0 = kMu0 * g.L0;
+  const double scale = te ? 1.0 : 1.0 / mu0;
+  lv.clear();
+  // level sizes
+  std::vector<std::pair<int64_t, int64_t>> sizes;
+  int64_t nx = g.Nx, ny = g.Ny;
+  sizes.push_back({nx, ny});
+  while ((int)sizes.size() < prm.max_levels) {
+    const int64_t cx = (nx + 1) / 2, cy = (ny + 1) / 2;
+    if (cx < prm.min_n || cy < prm.min_n || cx < 2 || cy < 2) break;
+    nx = cx; ny = cy; sizes.push_back({nx, ny});
+  }
+  lv.resize(sizes.size());
+  size_t scratch_need = 0, line_scratch_need = 0;
+  for (size_t l = 0; l < lv.size(); ++l) {
+    MGLevel<T>& L = lv[l];
+    L.nx = sizes[l].first; L.ny = sizes[l].second; L.stride = (int64_t)1 << l;
+    const int64_t N = L.nx * L.ny;
+    // 1-D coefficients
+    Coef1D hc;
+    if (l == 0) hc = op.hc; else host_coef_level(g, op.omega, op.ordering, scale, L.stride, L.nx, L.ny, hc);
+    std::vector<cplx<T>> pack; pack.reserve(2 * L.nx + 2 * L.ny);
+    for (auto* v : {&hc.cxm, &hc.cxp, &hc.cym, &hc.cyp}) for (auto& z : *v) pack.push_back(cplx<T>(T(z.real()), T(z.imag())));
+    CUDA_TRY(ctx, L.c1d.alloc(pack.size()));
+    CUDA_TRY(ctx, cudaMemcpyAsync(L.c1d.p, pack.data(), pack.size() * sizeof(cplx<T>), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    // eps of this level
+    const c128* eps_l = nullptr;
+    const int threads = 256;
+    if (l == 0) eps_l = op.eps.p;
+    else {
+      CUDA_TRY(ctx, L.eps.alloc(N));
+      const c128* eps_f = l == 1 ? op.eps.p : lv[l - 1].eps.p;
+      const int blocks = (int)std::min<int64_t>((N + threads - 1) / threads, (int64_t)ctx->num_sms * 16);
+      k_restrict_eps<<<blocks, threads, 0, ctx->stream>>>(lv[l - 1].nx, lv[l - 1].ny, L.nx, L.ny, eps_f, L.eps.p);
+      KLAUNCH(ctx);
+      eps_l = L.eps.p;
+    }
+    {
+      const int blocks = (int)std::min<int64_t>((N + threads - 1) / threads, (int64_t)ctx->num_sms * 16);
+      if (te) {
+        CUDA_TRY(ctx, L.gx.alloc(N)); CUDA_TRY(ctx, L.gy.alloc(N));
+        k_level_setup<T, true><<<blocks, threads, 0, ctx->stream>>>(L.nx, L.ny, eps_l, 0.0, prm.beta, eps0, nullptr, L.gx.p, L.gy.p);
+        const double m = op.omega * op.omega * mu0;
+        L.mass_const = cplx<T>(T(m), T(-prm.beta * m));
+      } else {
+        CUDA_TRY(ctx, L.mass.alloc(N));
+        k_level_setup<T, false><<<blocks, threads, 0, ctx->stream>>>(L.nx, L.ny, eps_l, op.omega * op.omega * eps0, prm.beta, eps0,
+                                                                   L.mass.p, nullptr, nullptr);
+      }
+      KLAUNCH(ctx);
+      CUDA_TRY(ctx, cudaGetLastError());
+    }
+    CUDA_TRY(ctx, L.u.alloc(N)); CUDA_TRY(ctx, L.f.alloc(N)); CUDA_TRY(ctx, L.tmp.alloc(N));
+    // PML strips of this level
+    auto strip = [&](int64_t npml, int64_t n) -> int {
+      if (npml == 0) return 0;
+      int64_t w = (npml + L.stride - 1) / L.stride + prm.pad;
+      return (int)std::min<int64_t>(w, n / 2);
+    };
+    L.npx = strip(g.Npml_x, L.nx); L.npy = strip(g.Npml_y, L.ny);
+    auto log2ceil = [](int64_t n) { int k = 0; while (((int64_t)1 << k) < n) ++k; return k; };
+    L.Ky = log2ceil(L.ny); L.Kx = log2ceil(L.nx);
+    if (L.npx > 0) {
+      CUDA_TRY(ctx, L.rxs.alloc((size_t)2 * L.npx * L.ny));
+      CUDA_TRY(ctx, L.pcr_y.alloc((size_t)2 * L.npx * (2 * L.Ky + 1) * L.ny));
+      scratch_need = std::max(scratch_need, (size_t)2 * L.npx * 6 * L.ny);
+      if ((size_t)2 * L.ny * sizeof(cplx<T>) > 200 * 1024) line_scratch_need = std::max(line_scratch_need, (size_t)2 * L.npx * 2 * L.ny);
+    }
+    if (L.npy > 0) {
+      CUDA_TRY(ctx, L.rys.alloc((size_t)2 * L.npy * L.nx));
+      CUDA_TRY(ctx, L.pcr_x.alloc((size_t)2 * L.npy * (2 * L.Kx + 1) * L.nx));
+      scratch_need = std::max(scratch_need, (size_t)2 * L.npy * 6 * L.nx);
+      if ((size_t)2 * L.nx * sizeof(cplx<T>) > 200 * 1024) line_scratch_need = std::max(line_scratch_need, (size_t)2 * L.npy * 2 * L.nx);
+    }
+  }
+  CUDA_TRY(ctx, spare.alloc((size_t)g.Nx * g.Ny));
+  CUDA_TRY(ctx, pcr_scratch.alloc(scratch_need));
+  if (line_scratch_need) CUDA_TRY(ctx, line_scratch.alloc(line_scratch_need));
+  for (size_t l = 0; l < lv.size(); ++l) {
+    MGLevel<T>& L = lv[l];
+    if (L.npx > 0) {
+      if (te) k_pcr_setup<T, true><<<2 * L.npx, 256, 0, ctx->stream>>>(L.view(), 0, L.npx, L.Ky, pcr_scratch.p, L.pcr_y.p);
+      else k_pcr_setup<T, false><<<2 * L.npx, 256, 0, ctx->stream>>>(L.view(), 0, L.npx, L.Ky, pcr_scratch.p, L.pcr_y.p);
+      KLAUNCH(ctx);
+    }
+    if (L.npy > 0) {
+      if (te) k_pcr_setup<T, true><<<2 * L.npy, 256, 0, ctx->stream>>>(L.view(), 1, L.npy, L.Kx, pcr_scratch.p, L.pcr_x.p);
+      else k_pcr_setup<T, false><<<2 * L.npy, 256, 0, ctx->stream>>>(L.view(), 1, L.npy, L.Kx, pcr_scratch.p, L.pcr_x.p);
+      KLAUNCH(ctx);
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+  }
+  // opt in to large dynamic shared memory for the line kernel
+  CUDA_TRY(ctx, cudaFuncSetAttribute(k_lines<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  pcr_scratch.release();
+  return FDFD_OK;
+}
+
+template <typename T> int Multigrid<T>::smooth(int l, bool zero) {
+  MGLevel<T>& L = lv[l];
+  const OpView<T> op = L.view();
+  dim3 grid((unsigned)((L.nx + kMgThreads - 1) / kMgThreads), (unsigned)((L.ny + kMgRows - 1) / kMgRows));
+  const T wj = T(prm.wjac), wl = T(prm.wline);
+  cplx<T>* out = zero ? L.u.p : L.tmp.p;
+#define SMOOTH(TEV, ZV) k_smooth_pt<T, TEV, ZV><<<grid, kMgThreads, 0, ctx->stream>>>(op, L.u.p, L.f.p, out, L.rxs.p, L.npx, L.npy, wj, done)
+  if (te) { if (zero) SMOOTH(true, true); else SMOOTH(true, false); }
+  else    { if (zero) SMOOTH(false, true); else SMOOTH(false, false); }
+#undef SMOOTH
+  KLAUNCH(ctx);
+  if (!zero) { std::swap(L.u.p, L.tmp.p); }  // u now holds the updated iterate
+  auto launch_lines = [&](int mode) {
+    const int64_t n = mode == 0 ? L.ny : L.nx;
+    const int np = mode == 0 ? L.npx : L.npy;
+    const int K = mode == 0 ? L.Ky : L.Kx;
+    const size_t smem = (size_t)2 * n * sizeof(cplx<T>);
+    const bool use_g = smem > 200 * 1024;
+    const int threads = (int)std::min<int64_t>(1024, std::max<int64_t>(32, ((n + 31) / 32) * 32));
+    k_lines<T><<<2 * np, threads, use_g ? 0 : smem, ctx->stream>>>(n, K, mode == 0 ? L.pcr_y.p : L.pcr_x.p,
+                                                                  mode == 0 ? L.rxs.p : L.rys.p, L.u.p, mode, L.nx, L.ny, np, wl,
+                                                                  use_g ? line_scratch.p : nullptr, done);
+    KLAUNCH(ctx);
+  };
+  if (L.npx > 0) launch_lines(0);
+  if (L.npy > 0) {
+    dim3 g2((unsigned)((L.nx + 127) / 128), (unsigned)(2 * L.npy));
+    if (te) k_resid_rows<T, true><<<g2, 128, 0, ctx->stream>>>(op, L.u.p, L.f.p, L.rys.p, L.npy, done);
+    else k_resid_rows<T, false><<<g2, 128, 0, ctx->stream>>>(op, L.u.p, L.f.p, L.rys.p, L.npy, done);
+    KLAUNCH(ctx);
+    launch_lines(1);
+  }
+  CUDA_TRY(ctx, cudaGetLastError());
+  return FDFD_OK;
+}
+
+// kind: 0 = V, 1 = F, 2 = W (W recursion only while l < wdepth)
+template <typename T> int Multigrid<T>::cycle(int l, bool zero, int kind) {
+  MGLevel<T>& L = lv[l];
+  if (l == (int)lv.size() - 1) {
+    for (int s = 0; s < std::max(1, prm.coarse_sweeps); ++s) FDFD_TRY(smooth(l, zero && s == 0));
+    return FDFD_OK;
+  }
+  for (int s = 0; s < std::max(1, prm.nu1); ++s) FDFD_TRY(smooth(l, zero && s == 0));
+  MGLevel<T>& C = lv[l + 1];
+  {
+    dim3 grid((unsigned)((C.nx + 127) / 128), (unsigned)C.ny);
+    if (te) k_resid_restrict<T, true><<<grid, 128, 0, ctx->stream>>>(L.view(), L.u.p, L.f.p, C.nx, C.ny, C.f.p, done);
+    else k_resid_restrict<T, false><<<grid, 128, 0, ctx->stream>>>(L.view(), L.u.p, L.f.p, C.nx, C.ny, C.f.p, done);
+    KLAUNCH(ctx);
+  }
+  if (kind == 2 && l < prm.wdepth) {
+    FDFD_TRY(cycle(l + 1, true, 2));
+    FDFD_TRY(cycle(l + 1, false, 2));
+  } else if (kind == 1) {
+    FDFD_TRY(cycle(l + 1, true, 1));
+    FDFD_TRY(cycle(l + 1, false, 0));
+  } else {
+    FDFD_TRY(cycle(l + 1, true, kind == 2 ? 0 : kind));
+  }
+  {
+    dim3 grid((unsigned)((L.nx + 127) / 128), (unsigned)L.ny);
+    k_prolong_add<T><<<grid, 128, 0, ctx->stream>>>(L.nx, L.ny, C.nx, C.ny, C.u.p, L.u.p, done);
+    KLAUNCH(ctx);
+  }
+  for (int s = 0; s < prm.nu2; ++s) FDFD_TRY(smooth(l, false));
+  CUDA_TRY(ctx, cudaGetLastError());
+  return FDFD_OK;
+}
+
+template <typename T> int Multigrid<T>::apply(const cplx<T>** out) {
+  FDFD_TRY(cycle(0, true, prm.cycle));
+  *out = lv[0].u.p;
+  return FDFD_OK;
+}
+
+template struct Multigrid<float>;
+template struct Multigrid<double>;

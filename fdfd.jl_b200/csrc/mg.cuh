@@ -1,0 +1,63 @@
+// mg.cuh -- matrix-free geometric multigrid on the complex-shifted operator
+//   M = L_pml + (1 - i beta) w^2 eps        (TM; TE shifts the constant w^2 mu0 term)
+// used as the right preconditioner of the Krylov solver (K8).  New work: the reference has no
+// iterative solver (src/solver/solver.jl:29-35 is a sparse direct LU).
+//
+// Design (calibrated in tools/mg_prototype.py):
+//  * vertex-centred coarsening  coarse I <-> fine 2I, any size (odd sizes leave a seam inside the PML),
+//    full-weighting restriction (1/2 P^T per axis), bilinear prolongation, re-discretised coarse operators
+//    whose 1-D PML coefficients sample the continuous s-profile of src/pml.jl:1-31 at the coarse points.
+//  * smoother: damped point Jacobi in the interior; inside the PML strips the stretched operator is
+//    strongly anisotropic with rotated phases and point smoothers amplify, so the strip columns get
+//    y-line relaxation and the strip rows x-line relaxation.  Line systems are solved by parallel cyclic
+//    reduction with multipliers precomputed at setup (only the right-hand side is reduced per sweep).
+//  * arithmetic in T = float (default; halves HBM traffic, the outer Krylov is fp64) or double.
+#pragma once
+#include "device_ops.cuh"
+
+template <typename T> struct MGLevel {
+  int64_t nx = 0, ny = 0, stride = 1;
+  int npx = 0, npy = 0;       // strip half-widths: columns [0,npx) U [nx-npx,nx), rows likewise
+  int Kx = 0, Ky = 0;         // PCR steps of x-lines (length nx) / y-lines (length ny)
+  DevBuf<cplx<T>> c1d, mass, gx, gy;
+  DevBuf<c128> eps;           // level eps_r (fp64), level 0 aliases the fine operator's copy (not owned)
+  DevBuf<cplx<T>> u, f, tmp;
+  DevBuf<cplx<T>> rxs, rys;   // strip residual buffers: [line][i]
+  DevBuf<cplx<T>> pcr_y, pcr_x;  // per line: alpha[K][n] | gamma[K][n] | binv[n]
+  cplx<T> mass_const{T(0), T(0)};
+  OpView<T> view() const {
+    OpView<T> v;
+    v.nx = nx; v.ny = ny;
+    v.cxm = c1d.p; v.cxp = c1d.p + nx; v.cym = c1d.p + 2 * nx; v.cyp = c1d.p + 2 * nx + ny;
+    v.mass = mass.p; v.gx = gx.p; v.gy = gy.p; v.mass_const = mass_const;
+    return v;
+  }
+};
+
+struct MGParams {
+  int cycle = FDFD_CYCLE_W, wdepth = 4, nu1 = 1, nu2 = 1, coarse_sweeps = 4;
+  double beta = 0.5, wjac = 0.8, wline = 0.7;
+  int min_n = 2, pad = 1, max_levels = 32;
+};
+
+template <typename T> struct Multigrid {
+  fdfd_ctx* ctx = nullptr;
+  bool te = false;
+  MGParams prm;
+  std::vector<MGLevel<T>> lv;
+  DevBuf<c128> pcr_scratch;   // setup-only scratch
+  DevBuf<cplx<T>> line_scratch;  // global ping-pong for lines too long for shared memory
+  DevBuf<cplx<T>> spare;         // third level-0 buffer: lets the caller keep one result across the next apply
+  const int* done = nullptr;     // optional device flag: kernels early-exit once the Krylov loop has converged
+
+  // build hierarchy for the operator `op` (fine eps_r resident in op.eps)
+  int setup(fdfd_ctx* ctx, const FineOp& op, const MGParams& prm);
+  // u0 = approx M^-1 f0 where f0 = lv[0].f (already filled).  Result pointer returned in *out (lv[0].u or .tmp)
+  int apply(const cplx<T>** out);
+  cplx<T>* rhs() { return lv[0].f.p; }
+  int levels() const { return (int)lv.size(); }
+
+ private:
+  int cycle(int l, bool zero, int kind);
+  int smooth(int l, bool zero);
+};

@@ -1,0 +1,250 @@
+// stencil.cu -- K4/K5 matrix-free complex128 Yee-stencil apply, K9 field recovery, operator setup.
+//
+// The apply kernel is the headline HBM-bound kernel: algorithmic traffic 48 B/point (TM: read x 16,
+// read mass 16, write y 16; 1-D PML coefficient arrays are L1/L2 resident).  Layout: x fastest, one thread
+// per x position (128-bit loads, a warp covers 512 contiguous bytes), each thread marches ROWS rows in y
+// and keeps the y-neighbours in registers, so every x value is fetched from L2/HBM once per row-block;
+// x+-1 neighbours come from the same 128 B lines through L1.
+#include "device_ops.cuh"
+#include "reduce.cuh"
+
+namespace {
+
+__global__ void k_setup_tm(int64_t N, double w2eps0, const c128* __restrict__ eps, c128* __restrict__ mass) {
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+    c128 e = eps[n];
+    mass[n] = c128(w2eps0 * e.x, w2eps0 * e.y);
+  }
+}
+
+// gx = 1 ./ grid_average(eps0*eps_r, x), gy likewise (grid.jl:157-162, driven.jl:22-23)
+__global__ void k_setup_te(int64_t Nx, int64_t Ny, double eps0, const c128* __restrict__ eps, c128* __restrict__ gx,
+                           c128* __restrict__ gy) {
+  const int64_t N = Nx * Ny;
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t ix = n % Nx, iy = n / Nx;
+    const int64_t ixm = ix == 0 ? Nx - 1 : ix - 1, iym = iy == 0 ? Ny - 1 : iy - 1;
+    c128 e = eps[n], ew = eps[ixm + Nx * iy], es = eps[ix + Nx * iym];
+    c128 a = c128(eps0 * e.x, eps0 * e.y);
+    c128 aw = c128(eps0 * ew.x, eps0 * ew.y), as = c128(eps0 * es.x, eps0 * es.y);
+    c128 avx = c128((a.x + aw.x) / 2, (a.y + aw.y) / 2);
+    c128 avy = c128((a.x + as.x) / 2, (a.y + as.y) / 2);
+    gx[n] = crecip(avx);
+    gy[n] = crecip(avy);
+  }
+}
+
+template <typename TI> __device__ __forceinline__ c128 ldx(const TI* p, int64_t i) { return c128(p[i]); }
+
+constexpr int kApplyThreads = 128;
+
+template <typename TI, bool TE, int NDOT, int ROWS>
+__global__ void __launch_bounds__(kApplyThreads)
+k_apply(OpView<double> op, const TI* __restrict__ x, c128* __restrict__ y, const c128* __restrict__ d0,
+        c128* __restrict__ partials, const int* __restrict__ done) {
+  if (done && *done) return;
+  const int64_t Nx = op.nx, Ny = op.ny;
+  const int64_t ix = blockIdx.x * (int64_t)kApplyThreads + threadIdx.x;
+  const int64_t iy0 = blockIdx.y * (int64_t)ROWS;
+  double acc[NDOT > 0 ? 2 * NDOT : 1];
+#pragma unroll
+  for (int k = 0; k < (NDOT > 0 ? 2 * NDOT : 1); ++k) acc[k] = 0.0;
+  if (ix < Nx) {
+    const int64_t ixm = ix == 0 ? Nx - 1 : ix - 1, ixp = ix + 1 == Nx ? 0 : ix + 1;
+    const c128 cw = op.cxm[ix], ce = op.cxp[ix];
+    int64_t iym = iy0 == 0 ? Ny - 1 : iy0 - 1;
+    c128 us = ldx(x, ix + Nx * iym);
+    c128 uc = ldx(x, ix + Nx * iy0);
+    c128 gyc = TE ? op.gy[ix + Nx * iy0] : c128(1.0, 0.0);
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const int64_t iy = iy0 + r;
+      if (iy >= Ny) break;
+      const int64_t iyp = iy + 1 == Ny ? 0 : iy + 1;
+      const int64_t n = ix + Nx * iy;
+      const c128 un = ldx(x, ix + Nx * iyp);
+      const c128 uw = ldx(x, ixm + Nx * iy), ue = ldx(x, ixp + Nx * iy);
+      c128 W = cw, E = ce, S = op.cym[iy], Nn = op.cyp[iy], m;
+      if (TE) {
+        const c128 gyn = op.gy[ix + Nx * iyp];
+        W = W * op.gx[n]; E = E * op.gx[ixp + Nx * iy];
+        S = S * gyc; Nn = Nn * gyn;
+        gyc = gyn;
+        m = op.mass_const;
+      } else {
+        m = op.mass[n];
+      }
+      // y = W uw + E ue + S us + N un + ((-(W+E) - (S+N)) + m) uc   (same association as the assembled matrix)
+      const c128 C = ((-W - E) + (-S - Nn)) + m;
+      c128 out = C * uc;
+      cfma(out, W, uw); cfma(out, E, ue); cfma(out, S, us); cfma(out, Nn, un);
+      y[n] = out;
+      if constexpr (NDOT == 1) {  // <d0, y> = sum conj(d0) y
+        const c128 d = d0[n];
+        const c128 p = cmulc(d, out);
+        acc[0] += p.x; acc[1] += p.y;
+      } else if constexpr (NDOT == 2) {  // <y, d0>, <y, y>
+        const c128 d = d0[n];
+        const c128 p = cmulc(out, d);
+        acc[0] += p.x; acc[1] += p.y;
+        acc[2] += norm2(out);
+      }
+      us = uc; uc = un;
+    }
+  }
+  if constexpr (NDOT > 0) {
+    const int64_t b = blockIdx.y * (int64_t)gridDim.x + blockIdx.x;
+    block_reduce_store<kApplyThreads, 2 * NDOT>(acc, reinterpret_cast<double*>(partials) + b * 2 * NDOT);
+  }
+}
+
+// K9: comp0 = u, comp1 = k1 * D1 u, comp2 = k2 * D2 u with D = stretched backward or forward differences.
+// TM: comp1 = kx * Dy u (hx), comp2 = ky * Dx u (hy).     driven.jl:40-41 (backward) / modulation.jl:112-113, eigen.jl:90-91 (forward)
+// TE: comp1 = k * g1 * Dyb u (ex), comp2 = k * g2 * (-Dxb u) (ey), (g1,g2) = (gy,gx) driven.jl:50-51 or (gx,gy) eigen.jl:108-109
+template <bool TE>
+__global__ void k_recover(int64_t Nx, int64_t Ny, const c128* __restrict__ u, const c128* __restrict__ sx,
+                          const c128* __restrict__ sy, double ax, double ay, int forward, c128 k1, c128 k2,
+                          const c128* __restrict__ g1, const c128* __restrict__ g2, c128* __restrict__ out) {
+  const int64_t N = Nx * Ny;
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t ix = n % Nx, iy = n / Nx;
+    const c128 uc = u[n];
+    c128 dxu, dyu;
+    if (forward) {
+      const int64_t ixp = ix + 1 == Nx ? 0 : ix + 1, iyp = iy + 1 == Ny ? 0 : iy + 1;
+      // row of S*δf: values s*(1/d)*(-1) on the diagonal and s*(1/d)*(+1) on the +1 neighbour
+      const c128 sxv = sx[ix], syv = sy[iy];
+      dxu = c128(sxv.x * -ax, sxv.y * -ax) * uc + c128(sxv.x * ax, sxv.y * ax) * u[ixp + Nx * iy];
+      dyu = c128(syv.x * -ay, syv.y * -ay) * uc + c128(syv.x * ay, syv.y * ay) * u[ix + Nx * iyp];
+    } else {
+      const int64_t ixm = ix == 0 ? Nx - 1 : ix - 1, iym = iy == 0 ? Ny - 1 : iy - 1;
+      const c128 sxv = sx[ix], syv = sy[iy];
+      dxu = c128(sxv.x * -ax, sxv.y * -ax) * u[ixm + Nx * iy] + c128(sxv.x * ax, sxv.y * ax) * uc;
+      dyu = c128(syv.x * -ay, syv.y * -ay) * u[ix + Nx * iym] + c128(syv.x * ay, syv.y * ay) * uc;
+    }
+    c128 c1, c2;
+    if (TE) { c1 = k1 * (g1[n] * dyu); c2 = k2 * (g2[n] * (-dxu)); }
+    else    { c1 = k1 * dyu; c2 = k2 * dxu; }
+    out[n] = uc; out[N + n] = c1; out[2 * N + n] = c2;
+  }
+}
+
+}  // namespace
+
+int FineOp::build(fdfd_ctx* ctx, const fdfd_grid_t& g_, int pol_, int ordering_, double omega_, const fdfd_c128* eps_r_any) {
+  g = g_; pol = pol_; ordering = ordering_; omega = omega_;
+  const int64_t N = g.Nx * g.Ny;
+  ARG_CHECK(ctx, !(pol == FDFD_TE && ordering != FDFD_ORDER_FB), "TE is defined for the f.b ordering only");
+  const double eps0 = kEps0 * g.L0, mu0 = kMu0 * g.L0;
+  // TM: mu0^-1 folded into the 1-D coefficients (driven.jl:35 `δxf*μ₀^-1*δxb`); TE: none (driven.jl:45)
+  host_coef_fine(g, omega, ordering, pol == FDFD_TM ? 1.0 / mu0 : 1.0, hc);
+  CUDA_TRY(ctx, c1d.alloc(2 * g.Nx + 2 * g.Ny));
+  std::vector<std::complex<double>> pack;
+  pack.insert(pack.end(), hc.cxm.begin(), hc.cxm.end()); pack.insert(pack.end(), hc.cxp.begin(), hc.cxp.end());
+  pack.insert(pack.end(), hc.cym.begin(), hc.cym.end()); pack.insert(pack.end(), hc.cyp.begin(), hc.cyp.end());
+  CUDA_TRY(ctx, cudaMemcpyAsync(c1d.p, pack.data(), pack.size() * sizeof(c128), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // pack is a local
+  CUDA_TRY(ctx, eps.alloc(N));
+  FDFD_TRY(fdfd_copy_in(ctx, eps.p, eps_r_any, N * sizeof(c128)));
+  const int threads = 256;
+  const int blocks = (int)std::min<int64_t>((N + threads - 1) / threads, (int64_t)ctx->num_sms * 16);
+  if (pol == FDFD_TM) {
+    CUDA_TRY(ctx, mass.alloc(N));
+    // ω^2*Tϵ with Tϵ = ϵ₀*ϵᵣ (driven.jl:21,35): (ω^2) * (eps0*eps) -- fold the two real factors
+    k_setup_tm<<<blocks, threads, 0, ctx->stream>>>(N, omega * omega * eps0, eps.p, mass.p);
+    KLAUNCH(ctx);
+  } else {
+    CUDA_TRY(ctx, gx.alloc(N)); CUDA_TRY(ctx, gy.alloc(N));
+    k_setup_te<<<blocks, threads, 0, ctx->stream>>>(g.Nx, g.Ny, eps0, eps.p, gx.p, gy.p);
+    KLAUNCH(ctx);
+    mass_const = c128(omega * omega * mu0, 0.0);
+  }
+  CUDA_TRY(ctx, cudaGetLastError());
+  return FDFD_OK;
+}
+
+template <typename TI, bool TE, int NDOT>
+static int launch_apply_t(fdfd_ctx* ctx, const OpView<double>& op, const TI* x, c128* y, const DotSpec& ds) {
+  constexpr int ROWS = 8;
+  dim3 grid((unsigned)((op.nx + kApplyThreads - 1) / kApplyThreads), (unsigned)((op.ny + ROWS - 1) / ROWS));
+  if (ds.nblocks_out) *ds.nblocks_out = (int)(grid.x * grid.y);
+  k_apply<TI, TE, NDOT, ROWS><<<grid, kApplyThreads, 0, ctx->stream>>>(op, x, y, ds.d0, ds.partials, ds.done);
+  KLAUNCH(ctx);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return FDFD_OK;
+}
+
+int apply_num_blocks(int64_t nx, int64_t ny) {
+  return (int)(((nx + kApplyThreads - 1) / kApplyThreads) * ((ny + 8 - 1) / 8));
+}
+
+int launch_apply(fdfd_ctx* ctx, const OpView<double>& op, bool te, const void* x, bool x_is_f32, c128* y, const DotSpec& ds) {
+#define DISPATCH(TI, TEV)                                                                        \
+  switch (ds.ndot) {                                                                             \
+    case 0: return launch_apply_t<TI, TEV, 0>(ctx, op, (const TI*)x, y, ds);                     \
+    case 1: return launch_apply_t<TI, TEV, 1>(ctx, op, (const TI*)x, y, ds);                     \
+    default: return launch_apply_t<TI, TEV, 2>(ctx, op, (const TI*)x, y, ds);                    \
+  }
+  if (x_is_f32) { if (te) { DISPATCH(c64, true) } else { DISPATCH(c64, false) } }
+  else          { if (te) { DISPATCH(c128, true) } else { DISPATCH(c128, false) } }
+#undef DISPATCH
+  return FDFD_OK;
+}
+
+int launch_recover(fdfd_ctx* ctx, const FineOp& op, const c128* u, int forward, std::complex<double> omega_field,
+                   int te_swap, c128* fields3) {
+  const fdfd_grid_t& g = op.g;
+  const int64_t N = g.Nx * g.Ny;
+  const double mu0 = kMu0 * g.L0;
+  // inverse s-factors of the requested difference direction, frozen at the operator's omega
+  std::vector<std::complex<double>> sx, sy;
+  host_sfactor(g, 0, forward, op.omega, sx); host_sfactor(g, 1, forward, op.omega, sy);
+  for (auto& z : sx) z = 1.0 / z;
+  for (auto& z : sy) z = 1.0 / z;
+  DevBuf<c128> ds;
+  CUDA_TRY(ctx, ds.alloc(g.Nx + g.Ny));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ds.p, sx.data(), g.Nx * sizeof(c128), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ds.p + g.Nx, sy.data(), g.Ny * sizeof(c128), cudaMemcpyHostToDevice, ctx->stream));
+  const std::complex<double> I(0.0, 1.0);
+  const int threads = 256;
+  const int blocks = (int)std::min<int64_t>((N + threads - 1) / threads, (int64_t)ctx->num_sms * 16);
+  if (op.pol == FDFD_TM) {
+    // hx = -1/1im/ω/μ₀ * Dy ez ; hy = 1/1im/ω/μ₀ * Dx ez   (left-to-right like Julia)
+    const std::complex<double> k1 = ((-1.0 / I) / omega_field) / mu0, k2 = ((1.0 / I) / omega_field) / mu0;
+    k_recover<false><<<blocks, threads, 0, ctx->stream>>>(g.Nx, g.Ny, u, ds.p, ds.p + g.Nx, 1.0 / grid_dx(g), 1.0 / grid_dy(g),
+                                                         forward, to_c128(k1), to_c128(k2), nullptr, nullptr, fields3);
+  } else {
+    // ex = 1/1im/ω * T1 * Dyb hz ; ey = 1/1im/ω * T2 * (-Dxb hz)
+    const std::complex<double> k = (1.0 / I) / omega_field;
+    const c128* g1 = te_swap ? op.gx.p : op.gy.p;
+    const c128* g2 = te_swap ? op.gy.p : op.gx.p;
+    k_recover<true><<<blocks, threads, 0, ctx->stream>>>(g.Nx, g.Ny, u, ds.p, ds.p + g.Nx, 1.0 / grid_dx(g), 1.0 / grid_dy(g),
+                                                        forward, to_c128(k), to_c128(k), g1, g2, fields3);
+  }
+  KLAUNCH(ctx);
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // ds, sx, sy are locals
+  return FDFD_OK;
+}
+
+extern "C" int fdfd_apply_operator(fdfd_ctx* ctx, const fdfd_grid_t* g, int pol, int ordering, double omega,
+                                   const fdfd_c128* eps_r, const fdfd_c128* x, fdfd_c128* y) {
+  ARG_CHECK(ctx, ctx != nullptr, "ctx is NULL");
+  FDFD_TRY(check_grid(ctx, g));
+  ARG_CHECK(ctx, pol == FDFD_TM || pol == FDFD_TE, "pol must be FDFD_TM or FDFD_TE");
+  ARG_CHECK(ctx, ordering == FDFD_ORDER_FB || ordering == FDFD_ORDER_BF, "bad ordering");
+  ARG_CHECK(ctx, eps_r && x && y, "NULL argument");
+  ARG_CHECK(ctx, omega > 0, "omega must be > 0");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const int64_t N = g->Nx * g->Ny;
+  FineOp op;
+  FDFD_TRY(op.build(ctx, *g, pol, ordering, omega, eps_r));
+  DevBuf<c128> dx, dy;
+  CUDA_TRY(ctx, dx.alloc(N)); CUDA_TRY(ctx, dy.alloc(N));
+  FDFD_TRY(fdfd_copy_in(ctx, dx.p, x, N * sizeof(c128)));
+  DotSpec ds;
+  FDFD_TRY(launch_apply(ctx, op.view(), pol == FDFD_TE, dx.p, false, dy.p, ds));
+  FDFD_TRY(fdfd_copy_out(ctx, y, dy.p, N * sizeof(c128)));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return FDFD_OK;
+}

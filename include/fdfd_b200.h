@@ -1,0 +1,180 @@
+/* fdfd_b200.h -- C ABI of the B200-native FDFD.jl assembly + linear-solve hot path.
+ *
+ * Drop-in boundary.  The reference (fancompute/FDFD.jl, pure Julia) has
+ * one plug-in seam, `dolinearsolve(A, b, sym)` (src/solver/solver.jl:4), but assembly is
+ * part of the path and the GPU solver is matrix-free, so the entry points below replace the
+ * L3 functions one level higher; each cites the reference code it stands in for.  A Julia
+ * maintainer binds them with `ccall`; tests bind them with ctypes.
+ *
+ * Conventions
+ *   - complex128 == two adjacent doubles (Julia ComplexF64 / C double _Complex / double2).
+ *   - all grid arrays are column-major (Nx,Ny) with x fastest: n = ix + Nx*iy  (Julia `a[:]`).
+ *   - field outputs are (Nx,Ny,3) column-major, components [Ez,Hx,Hy] (TM) / [Hz,Ex,Ey] (TE)
+ *     exactly like FieldTM/FieldTE.data (src/data.jl:50-78).
+ *   - every buffer is caller-owned; pointers may be host (pageable or pinned) or device
+ *     pointers (detected with cudaPointerGetAttributes).  Nothing is retained after return
+ *     except inside an explicit fdfd_problem handle, which copies what it needs.
+ *   - every function returns 0 on success, non-zero on error (message: fdfd_last_error).
+ *     No C++ exception crosses the boundary.  There is NO CPU fallback: without a CUDA
+ *     device every compute entry point fails with FDFD_ERR_CUDA.
+ */
+#ifndef FDFD_B200_H
+#define FDFD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FDFD_B200_ABI_VERSION 1
+
+/* status codes */
+enum {
+  FDFD_OK = 0,
+  FDFD_ERR_ARG = 1,      /* bad argument */
+  FDFD_ERR_CUDA = 2,     /* CUDA runtime error / no device */
+  FDFD_ERR_NOCONV = 3,   /* Krylov solver hit maxit (results still written, see info) */
+  FDFD_ERR_BREAKDOWN = 4,/* Krylov breakdown that restarts could not cure */
+  FDFD_ERR_ALLOC = 5
+};
+
+/* src/types.jl:20 */
+enum { FDFD_TM = 1, FDFD_TE = 2 };
+/* operator ordering: f.b = Dxf*Dxb (src/solver/driven.jl:35, eigen.jl:84,102),
+ *                    b.f = Dxb*Dxf (src/solver/modulation.jl:82) */
+enum { FDFD_ORDER_FB = 0, FDFD_ORDER_BF = 1 };
+/* derivative selector for fdfd_assemble_derivative (src/grid.jl:128-154) */
+enum { FDFD_DXF = 0, FDFD_DXB = 1, FDFD_DYF = 2, FDFD_DYB = 3 };
+/* sparse formats: CSR (row pointers) or CSC (Julia SparseMatrixCSC: colptr,rowval,nzval) */
+enum { FDFD_CSR = 0, FDFD_CSC = 1 };
+/* Krylov solvers / preconditioners */
+enum { FDFD_SOLVER_BICGSTAB = 0, FDFD_SOLVER_COCG = 1, FDFD_SOLVER_GMRES = 2 };
+enum { FDFD_PRECOND_NONE = 0, FDFD_PRECOND_JACOBI = 1, FDFD_PRECOND_MG = 2 };
+enum { FDFD_MG_F32 = 0, FDFD_MG_F64 = 1 };
+enum { FDFD_CYCLE_V = 0, FDFD_CYCLE_F = 1, FDFD_CYCLE_W = 2 };
+/* eigenfrequency `which` (Arpack semantics on the shift-inverted spectrum, eigen.jl:86) */
+enum { FDFD_WHICH_LM = 0, FDFD_WHICH_LR = 1, FDFD_WHICH_SR = 2, FDFD_WHICH_LI = 3, FDFD_WHICH_SI = 4 };
+
+typedef struct { double re, im; } fdfd_c128;
+
+/* POD mirror of Grid{2} (src/grid.jl:7-13); N is computed by the caller exactly as the
+ * reference constructor does (round(L/dh), src/grid.jl:28).  dx = (x1-x0)/Nx (grid.jl:68). */
+typedef struct {
+  int64_t Nx, Ny;
+  int64_t Npml_x, Npml_y;
+  double x0, x1, y0, y1;
+  double L0;
+} fdfd_grid_t;
+
+typedef struct {
+  int32_t solver;        /* FDFD_SOLVER_*  (default BICGSTAB) */
+  int32_t precond;       /* FDFD_PRECOND_* (default MG) */
+  double  tol;           /* relative residual ||b-Ax||/||b|| of the un-preconditioned system (default 1e-10) */
+  int32_t maxit;         /* Krylov iterations (default 20000) */
+  int32_t mg_precision;  /* FDFD_MG_F32 | FDFD_MG_F64 (default F32) */
+  int32_t mg_cycle;      /* FDFD_CYCLE_* (default W, truncated at mg_wdepth) */
+  int32_t mg_wdepth;     /* levels [0,wdepth) recurse twice in a W cycle (default 4) */
+  int32_t mg_nu1, mg_nu2;/* pre/post smoothing sweeps (default 1,1) */
+  int32_t mg_coarse_sweeps; /* sweeps on the coarsest level (default 4) */
+  double  mg_beta;       /* complex shift: M = L + (1 - i*beta) w^2 eps (default 0.5) */
+  double  mg_wjac;       /* point-Jacobi damping (default 0.8) */
+  double  mg_wline;      /* PML line-relaxation damping (default 0.7) */
+  int32_t check_every;   /* host polls convergence every k iterations (default 8) */
+  int32_t verbose;
+} fdfd_solve_opts_t;
+
+typedef struct {
+  int32_t iters;         /* Krylov iterations used */
+  int32_t flag;          /* FDFD_OK | FDFD_ERR_NOCONV | FDFD_ERR_BREAKDOWN */
+  double  relres;        /* final TRUE relative residual, recomputed with the fp64 operator */
+  double  setup_ms;      /* coefficient + MG hierarchy build (device) */
+  double  solve_ms;      /* Krylov loop, CUDA events on the ctx stream */
+  double  total_ms;      /* wall time of the call incl. host<->device copies */
+  int64_t launches;      /* kernels launched by this call */
+  int32_t restarts;
+  int32_t mg_levels;
+} fdfd_info_t;
+
+typedef struct fdfd_ctx fdfd_ctx;
+typedef struct fdfd_problem fdfd_problem;
+
+/* ---- context -------------------------------------------------------------------------- */
+int fdfd_abi_version(void);
+/* device: CUDA ordinal.  stream: an existing cudaStream_t to launch on (e.g. torch's current
+ * stream) or NULL to let the library create its own non-blocking stream. */
+int fdfd_ctx_create(int device, void* stream, fdfd_ctx** out);
+void fdfd_ctx_destroy(fdfd_ctx* ctx);
+const char* fdfd_last_error(fdfd_ctx* ctx);   /* ctx may be NULL: last global error */
+int64_t fdfd_launch_count(fdfd_ctx* ctx);     /* kernels launched since ctx creation */
+void fdfd_default_opts(fdfd_solve_opts_t* opts);
+
+/* ---- K1: PML s-factors.  Replaces create_sfactor (src/pml.jl:1-31): writes the four 1-D
+ * arrays s (NOT inverted), lengths Nx,Nx,Ny,Ny, order (x fwd, x bwd, y fwd, y bwd). */
+int fdfd_sfactors(fdfd_ctx* ctx, const fdfd_grid_t* g, double omega,
+                  fdfd_c128* sxf, fdfd_c128* sxb, fdfd_c128* syf, fdfd_c128* syb);
+
+/* ---- K2: Yee derivative operators assembled on the GPU straight into CSR/CSC.
+ * Replaces δ(w,s,g) (src/grid.jl:128-154) and, with stretched!=0, the row scaling by the
+ * inverse s-factors `Sxb*δ(...)` (src/pml.jl:33-63, src/solver/driven.jl:28-31).
+ * ptr has N+1 entries, ind/val have 2N entries; index_base is 0 or 1 (Julia). */
+int fdfd_assemble_derivative(fdfd_ctx* ctx, const fdfd_grid_t* g, double omega, int which,
+                             int stretched, int format, int index_base,
+                             int64_t* ptr, int64_t* ind, fdfd_c128* val);
+
+/* ---- K3: system matrix assembled on the GPU into CSR/CSC (5 nnz per row).
+ * pol=TM, FB : A = Dxf*mu0^-1*Dxb + Dyf*mu0^-1*Dyb + w^2*diag(eps0*eps_r)   (driven.jl:35)
+ * pol=TM, BF : A = Dxb/mu0*Dxf + Dyb/mu0*Dyf + w^2*diag(eps0*eps_r)         (modulation.jl:82,85)
+ * pol=TE, FB : A = Dxf*diag(1/avgx)*Dxb + Dyf*diag(1/avgy)*Dyb + w^2*mu0*I  (driven.jl:45)
+ * ptr: N+1, ind/val: 5N. */
+int fdfd_assemble_system(fdfd_ctx* ctx, const fdfd_grid_t* g, int pol, int ordering, double omega,
+                         const fdfd_c128* eps_r, int format, int index_base,
+                         int64_t* ptr, int64_t* ind, fdfd_c128* val);
+
+/* ---- K4/K5: matrix-free operator apply y = A x (same A as fdfd_assemble_system), host or
+ * device buffers.  Kernel-level parity hook. */
+int fdfd_apply_operator(fdfd_ctx* ctx, const fdfd_grid_t* g, int pol, int ordering, double omega,
+                        const fdfd_c128* eps_r, const fdfd_c128* x, fdfd_c128* y);
+
+/* ---- driven solve.  Replaces solve(d::Device, pol) (src/solver/driven.jl:4-59) for n_omega
+ * frequencies sharing eps_r; src is (Nx,Ny) per frequency when src_per_omega!=0 else shared.
+ * b = i*w*src (driven.jl:36).  fields: n_omega x (Nx,Ny,3).  info: n_omega entries. */
+int fdfd_solve_driven(fdfd_ctx* ctx, const fdfd_grid_t* g, int pol, int n_omega, const double* omega,
+                      const fdfd_c128* eps_r, const fdfd_c128* src, int src_per_omega,
+                      const fdfd_solve_opts_t* opts, fdfd_c128* fields, fdfd_info_t* info);
+
+/* ---- modulated multi-frequency solve.  Replaces solve(d::ModulatedDevice)
+ * (src/solver/modulation.jl:35-119) for one w: nf = 2*nsidebands+1 coupled sidebands,
+ * fields: nf x (Nx,Ny,3) (sideband -ns first), H from forward differences (:112-113). */
+int fdfd_solve_modulated(fdfd_ctx* ctx, const fdfd_grid_t* g, double omega, double Omega, int nsidebands,
+                         int sharedpml, const fdfd_c128* eps_r, const fdfd_c128* deps_r,
+                         const fdfd_c128* src, const fdfd_solve_opts_t* opts,
+                         fdfd_c128* fields, fdfd_info_t* info);
+
+/* ---- eigenfrequency.  Replaces eigenfrequency(d, pol, nev; which) (src/solver/eigen.jl:69-115):
+ * shift-invert Arnoldi around sigma = -w0^2 mu0 eps0 (TM) / -w0^2 mu0 (TE) with the PML frozen
+ * at w0; the inner solves reuse the driven operator.  omega_out: nev complex; fields: nev x (Nx,Ny,3)
+ * (may be NULL).  ncv<=0 picks max(20, 2*nev+1) like Arpack.jl. */
+int fdfd_eigenfrequency(fdfd_ctx* ctx, const fdfd_grid_t* g, int pol, double omega0, int nev, int which,
+                        int ncv, const fdfd_c128* eps_r, const fdfd_solve_opts_t* opts,
+                        fdfd_c128* omega_out, fdfd_c128* fields, fdfd_info_t* info);
+
+/* ---- resident-problem handle (what the one-shot calls are built from; lets a sweep keep
+ * eps_r, coefficients and the multigrid hierarchy in HBM between solves). */
+int fdfd_problem_create(fdfd_ctx* ctx, const fdfd_grid_t* g, int pol, int ordering, double omega,
+                        const fdfd_c128* eps_r, const fdfd_solve_opts_t* opts, fdfd_problem** out);
+void fdfd_problem_destroy(fdfd_problem* p);
+int fdfd_problem_set_rhs(fdfd_problem* p, const fdfd_c128* b);            /* b as is */
+int fdfd_problem_set_source(fdfd_problem* p, const fdfd_c128* src);       /* b = i*w*src */
+int fdfd_problem_solve(fdfd_problem* p, fdfd_info_t* info);               /* device-resident */
+int fdfd_problem_get_solution(fdfd_problem* p, fdfd_c128* x);             /* (Nx,Ny) */
+int fdfd_problem_get_fields(fdfd_problem* p, int forward_h, fdfd_c128* fields); /* (Nx,Ny,3) */
+/* timed loop of nrep matrix-free applies on resident data; ms_per_apply from CUDA events */
+int fdfd_problem_bench_apply(fdfd_problem* p, int nrep, double* ms_per_apply);
+/* one application of the preconditioner M^-1 to a resident vector (parity/debug hook) */
+int fdfd_problem_precond(fdfd_problem* p, const fdfd_c128* in, fdfd_c128* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDFD_B200_H */

@@ -1,0 +1,194 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI, against the CPU
+oracle on the same inputs.  Tolerances (BASELINE.json north_star): CSR/CSC indices bit-exact, operator values
+<= 1e-14 relative, solved fields <= 1e-6 relative L2 at a 1e-10 relative residual."""
+import math
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import fdfd_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+W200 = 2 * math.pi * 200e12
+VAL_TOL = 1e-14   # relative, operator values
+FIELD_TOL = 1e-6  # relative L2, solved fields
+RES_TOL = 1e-10   # relative residual
+
+
+def grids():
+    return [
+        (0.05, [6, 5], [0, 2.0], [0, 1.5]),          # 40 x 30, tiny
+        (0.02, [15, 10], [0.0, 4.0], [-1.0, 1.0]),   # 200 x 100
+        (0.03, [0, 7], [0, 1.5], [0, 2.1]),          # 50 x 70, no PML in x
+        (0.0301, [9, 9], [0, 2.0], [0, 1.7]),        # L/dh not an integer: dx != dh (grid.jl:28,68)
+    ]
+
+
+def rand_eps(shape, seed=0, lossy=False):
+    rng = np.random.default_rng(seed)
+    e = 1 + 11 * rng.random(shape)
+    return e + (0.3j * rng.random(shape) if lossy else 0j)
+
+
+def rel(a, b):
+    return np.linalg.norm(np.ravel(a) - np.ravel(b)) / np.linalg.norm(np.ravel(b))
+
+
+def maxrel(a, b):
+    """max entrywise relative error, entries compared as complex numbers"""
+    a, b = np.ravel(a), np.ravel(b)
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+
+
+@pytest.mark.parametrize("gargs", grids())
+def test_sfactors(fdfd, gargs):
+    g, go = fdfd.Grid(*gargs), O.Grid2D(*gargs)
+    got = fdfd.sfactors(g, W200)
+    ref = [O.create_sfactor(O.X, O.FORWARD, go, W200), O.create_sfactor(O.X, O.BACKWARD, go, W200),
+           O.create_sfactor(O.Y, O.FORWARD, go, W200), O.create_sfactor(O.Y, O.BACKWARD, go, W200)]
+    for a, b in zip(got, ref):
+        assert maxrel(a, b) <= VAL_TOL
+
+
+@pytest.mark.parametrize("gargs", grids())
+@pytest.mark.parametrize("stretched", [False, True])
+def test_derivative_csr_csc(fdfd, gargs, stretched):
+    g, go = fdfd.Grid(*gargs), O.Grid2D(*gargs)
+    if stretched:
+        dxb, dxf, dyb, dyf = O.scaled_derivatives(go, W200)
+    else:
+        dxb, dxf, dyb, dyf = (O.delta(O.X, O.BACKWARD, go), O.delta(O.X, O.FORWARD, go),
+                              O.delta(O.Y, O.BACKWARD, go), O.delta(O.Y, O.FORWARD, go))
+    refs = {fdfd._lib.DXF: dxf, fdfd._lib.DXB: dxb, fdfd._lib.DYF: dyf, fdfd._lib.DYB: dyb}
+    for which, ref in refs.items():
+        for fmt, conv in ((fdfd._lib.CSR, sp.csr_matrix), (fdfd._lib.CSC, sp.csc_matrix)):
+            r = conv(ref); r.sort_indices()
+            assert r.nnz == 2 * len(go)
+            for base in (0, 1):
+                p, ind, val = fdfd.assemble_derivative(g, W200, which, stretched, fmt, base)
+                assert np.array_equal(p, r.indptr.astype(np.int64) + base)      # bit-exact
+                assert np.array_equal(ind, r.indices.astype(np.int64) + base)   # bit-exact
+                assert maxrel(val, r.data) <= VAL_TOL
+
+
+@pytest.mark.parametrize("gargs", grids())
+@pytest.mark.parametrize("case", ["tm_fb", "tm_bf", "te_fb"])
+def test_system_matrix_and_apply(fdfd, gargs, case):
+    g, go = fdfd.Grid(*gargs), O.Grid2D(*gargs)
+    eps = rand_eps(go.size(), 1, lossy=True)
+    d = O.Device(go, [W200]); d.eps_r = eps
+    eps0, mu0, _ = O.normalize_parameters(go)
+    if case == "tm_fb":
+        A, _, _ = O.system_matrix(d, W200, O.TM); pol, order = fdfd.TM, fdfd._lib.ORDER_FB
+    elif case == "te_fb":
+        A, _, _ = O.system_matrix(d, W200, O.TE); pol, order = fdfd.TE, fdfd._lib.ORDER_FB
+    else:
+        md = O.ModulatedDevice(go, [W200], Omega=1e14, nsidebands=0); md.eps_r = eps
+        A, _, _, _, _ = O.modulated_system(md, W200); pol, order = fdfd.TM, fdfd._lib.ORDER_BF
+    for fmt, conv in ((fdfd._lib.CSR, sp.csr_matrix), (fdfd._lib.CSC, sp.csc_matrix)):
+        r = conv(A); r.sort_indices()
+        assert r.nnz == 5 * len(go)  # pattern is value independent
+        p, ind, val = fdfd.assemble_system(g, pol, W200, eps, order, fmt, 1)
+        assert np.array_equal(p, r.indptr.astype(np.int64) + 1)
+        assert np.array_equal(ind, r.indices.astype(np.int64) + 1)
+        assert maxrel(val, r.data) <= VAL_TOL
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal(go.size()) + 1j * rng.standard_normal(go.size())
+    y = fdfd.apply_operator(g, pol, W200, eps, x, order)
+    ref = (A @ x.ravel(order="F")).reshape(go.size(), order="F")
+    assert rel(y, ref) <= VAL_TOL
+
+
+def _oracle_device(go, d):
+    do = O.Device(go, list(d.omega))
+    do.eps_r[:] = d.eps_r
+    do.src[:] = d.src
+    return do
+
+
+def test_solve_tm_dipole(fdfd):
+    """notebook Example 1 geometry at dh=0.03 (200x200): point dipole in vacuum."""
+    gargs = (0.03, [15, 15], [-3, 3], [-3, 3])
+    g, go = fdfd.Grid(*gargs), O.Grid2D(*gargs)
+    d = fdfd.Device(g, W200)
+    fdfd.setup_src(d, fdfd.Point(0, 0))
+    f = fdfd.solve(d)
+    assert f.info["flag"] == 0 and f.info["relres"] <= RES_TOL
+    fo = O.solve(_oracle_device(go, d), O.TM)
+    assert rel(f.data, fo["data"]) <= FIELD_TOL
+    for k in range(3):
+        assert rel(f.data[:, :, k], fo["data"][:, :, k]) <= FIELD_TOL
+
+
+def test_solve_tm_waveguide_mode_source(fdfd):
+    """test/runtests.jl:23-38 / notebook Example 2: 500x100, eps=12 slab, mode source (launched on the host)."""
+    gargs = (0.02, [15, 10], [0.0, 10.0], [-1.0, 1.0])
+    g, go = fdfd.Grid(*gargs), O.Grid2D(*gargs)
+    d = fdfd.Device(g, W200)
+    fdfd.setup_eps_r(d, [fdfd.Box((5.0, 0.0), (np.inf, 0.3), 12)])
+    fdfd.add_mode(d, fdfd.Mode(fdfd.TM, fdfd.XHAT, 3.5, fdfd.Point(1.0, 0), 0.8))
+    f = fdfd.solve(d)
+    assert f.info["flag"] == 0 and f.info["relres"] <= RES_TOL
+    do = O.Device(go, [W200]); do.eps_r[:] = d.eps_r; do.modes.append(O.Mode(O.TM, O.X, 3.5, (1.0, 0), 0.8))
+    fo = O.solve(do, O.TM)
+    assert rel(f.data, fo["data"]) <= FIELD_TOL
+    # the consumer (flux.jl:37-47) sees the same number
+    fl = fdfd.flux_surface_integral(f, fdfd.Point(5.0, 0), np.inf, fdfd.XHAT)
+    flo = O.flux_surface_integral_tm_x(go, fo["data"], (5.0, 0), np.inf)
+    assert abs(fl / flo - 1) < 1e-6
+
+
+def test_solve_te_slab(fdfd):
+    gargs = (0.02, [15, 15], [0.0, 5.0], [-1.5, 1.5])
+    g, go = fdfd.Grid(*gargs), O.Grid2D(*gargs)
+    d = fdfd.Device(g, W200)
+    fdfd.setup_eps_r(d, lambda x, y: abs(y) <= 0.2, 12.25)
+    fdfd.setup_src(d, fdfd.Point(1.0, 0.0))
+    f = fdfd.solve(d, fdfd.TE)
+    assert f.info["flag"] == 0 and f.info["relres"] <= RES_TOL
+    fo = O.solve(_oracle_device(go, d), O.TE)
+    assert rel(f.data, fo["data"]) <= FIELD_TOL
+
+
+def test_solve_sweep_returns_list(fdfd):
+    gargs = (0.04, [10, 10], [0, 4.0], [0, 3.0])
+    g, go = fdfd.Grid(*gargs), O.Grid2D(*gargs)
+    ws = [2 * math.pi * f for f in (180e12, 200e12, 220e12)]
+    d = fdfd.Device(g, ws)
+    fdfd.setup_eps_r(d, [fdfd.Cylinder((2.0, 1.5), 0.6, 6.0)])
+    fdfd.setup_src(d, fdfd.Point(0.8, 1.5), fdfd.XHAT)
+    fs = fdfd.solve(d)
+    assert isinstance(fs, list) and len(fs) == 3
+    fos = O.solve(_oracle_device(go, d), O.TM)
+    for f, fo, w in zip(fs, fos, ws):
+        assert f.omega == complex(w) and f.info["relres"] <= RES_TOL
+        assert rel(f.data, fo["data"]) <= FIELD_TOL
+
+
+@pytest.mark.parametrize("mgprec", [0, 1])
+@pytest.mark.parametrize("cycle", [0, 1, 2])
+def test_solver_options(fdfd, mgprec, cycle):
+    """odd sizes (seams in the coarsening), every cycle type, fp32 and fp64 multigrid."""
+    gargs = (0.02, [15, 12], [0.0, 3.74], [0, 2.5])  # 187 x 125
+    g, go = fdfd.Grid(*gargs), O.Grid2D(*gargs)
+    d = fdfd.Device(g, W200)
+    d.eps_r = rand_eps(g.N, 3).real.round() + 0j
+    fdfd.setup_src(d, fdfd.Point(1.0, 1.2))
+    f = fdfd.solve(d, fdfd.TM, mg_precision=mgprec, mg_cycle=cycle)
+    assert f.info["flag"] == 0 and f.info["relres"] <= RES_TOL
+    fo = O.solve(_oracle_device(go, d), O.TM)
+    assert rel(f.data, fo["data"]) <= FIELD_TOL
+
+
+def test_zero_source_and_bad_args(fdfd):
+    g = fdfd.Grid(0.05, [5, 5], [0, 2.0], [0, 2.0])
+    d = fdfd.Device(g, W200)
+    f = fdfd.solve(d)  # b = 0 -> fields exactly zero, no iterations
+    assert f.info["iters"] == 0 and not np.any(f.data)
+    bad = fdfd.Grid(0.05, [30, 5], [0, 2.0], [0, 2.0])  # PML thicker than the grid
+    with pytest.raises(fdfd.FdfdError):
+        fdfd.solve(fdfd.Device(bad, W200))
+    with pytest.raises(fdfd.FdfdError):
+        fdfd.apply_operator(g, 7, W200, d.eps_r, d.src)
