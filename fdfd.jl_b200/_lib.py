@@ -32,7 +32,8 @@ class SolveOpts(C.Structure):
                 ("mg_precision", C.c_int32), ("mg_cycle", C.c_int32), ("mg_wdepth", C.c_int32),
                 ("mg_nu1", C.c_int32), ("mg_nu2", C.c_int32), ("mg_coarse_sweeps", C.c_int32),
                 ("mg_beta", C.c_double), ("mg_wjac", C.c_double), ("mg_wline", C.c_double),
-                ("check_every", C.c_int32), ("verbose", C.c_int32)]
+                ("check_every", C.c_int32), ("verbose", C.c_int32),
+                ("mg_shift_growth", C.c_double), ("mg_max_levels", C.c_int32), ("use_graph", C.c_int32)]
 
 
 class Info(C.Structure):
@@ -59,7 +60,7 @@ EXPORTS = [
     "fdfd_apply_operator", "fdfd_solve_driven", "fdfd_solve_modulated", "fdfd_eigenfrequency",
     "fdfd_problem_create", "fdfd_problem_destroy", "fdfd_problem_set_rhs", "fdfd_problem_set_source",
     "fdfd_problem_solve", "fdfd_problem_get_solution", "fdfd_problem_get_fields", "fdfd_problem_bench_apply",
-    "fdfd_problem_precond",
+    "fdfd_problem_precond", "fdfd_debug_hess_eig",
 ]
 
 
@@ -99,6 +100,7 @@ def lib():
         L.fdfd_problem_get_fields.argtypes = [vp, i32, vp]
         L.fdfd_problem_bench_apply.argtypes = [vp, i32, C.POINTER(dbl)]
         L.fdfd_problem_precond.argtypes = [vp, vp, vp]
+        L.fdfd_debug_hess_eig.argtypes = [i32, vp, vp, vp]
         _lib = L
     return _lib
 

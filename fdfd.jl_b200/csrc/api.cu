@@ -18,8 +18,8 @@ __global__ void k_fill_random(int64_t N, c128* __restrict__ x, uint64_t seed) {
   }
 }
 
-template <typename T> __global__ void k_cast_in(int64_t N, const c128* __restrict__ in, cplx<T>* __restrict__ out) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) out[i] = cplx<T>(in[i]);
+template <typename T> __global__ void k_cast_in(int64_t N, const c128* __restrict__ in, cplx<T>* __restrict__ out, double sc) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) out[i] = cplx<T>(c128(sc * in[i].x, sc * in[i].y));
 }
 template <typename T> __global__ void k_cast_out(int64_t N, const cplx<T>* __restrict__ in, c128* __restrict__ out) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) out[i] = c128(in[i]);
@@ -33,13 +33,12 @@ int vec_blocks(fdfd_ctx* ctx, int64_t N) { return (int)std::min<int64_t>((N + 25
 
 }  // namespace
 
-int apply_num_blocks(int64_t nx, int64_t ny);
-
-static MGParams mg_params_from(const fdfd_solve_opts_t& o) {
+MGParams mg_params_from(const fdfd_solve_opts_t& o) {
   MGParams m;
   m.cycle = o.mg_cycle; m.wdepth = o.mg_wdepth; m.nu1 = std::max(1, o.mg_nu1); m.nu2 = std::max(0, o.mg_nu2);
   m.coarse_sweeps = std::max(1, o.mg_coarse_sweeps);
   m.beta = o.mg_beta; m.wjac = o.mg_wjac; m.wline = o.mg_wline;
+  m.shift_growth = o.mg_shift_growth; if (o.mg_max_levels > 0) m.max_levels = o.mg_max_levels;
   return m;
 }
 
@@ -63,20 +62,12 @@ extern "C" int fdfd_problem_create(fdfd_ctx* ctx, const fdfd_grid_t* g, int pol,
   if (st != FDFD_OK) { delete P; return st; }
   const int64_t N = g->Nx * g->Ny;
   auto fail = [&](int code) { delete P; return code; };
-#define PALLOC(buf, n) do { if ((buf).alloc(n) != cudaSuccess) { fdfd_set_error(ctx, "out of device memory allocating %zu elements", (size_t)(n)); return fail(FDFD_ERR_ALLOC); } } while (0)
-  PALLOC(P->b, N); PALLOC(P->x, N); PALLOC(P->r, N); PALLOC(P->rhat, N); PALLOC(P->p, N); PALLOC(P->v, N); PALLOC(P->s, N); PALLOC(P->t, N);
-  if (P->opts.precond == FDFD_PRECOND_JACOBI) { PALLOC(P->ph, N); PALLOC(P->sh, N); }
-  P->nvec_blocks = vec_blocks(ctx, N);
-  const int nparts = std::max(P->nvec_blocks, apply_num_blocks(g->Nx, g->Ny));
-  PALLOC(P->partials, (size_t)nparts * 2);
-  PALLOC(P->scal, 1);
-  PALLOC(P->hist, (size_t)std::max(16, P->opts.maxit + 2));
-#undef PALLOC
-  if (cudaMallocHost((void**)&P->h_scal, sizeof(KScal)) != cudaSuccess) { fdfd_set_error(ctx, "cudaMallocHost failed"); return fail(FDFD_ERR_ALLOC); }
+  st = P->w.alloc(ctx, N, apply_num_blocks(g->Nx, g->Ny), P->opts.maxit, P->opts.precond == FDFD_PRECOND_JACOBI);
+  if (st != FDFD_OK) return fail(st);
   if (P->opts.precond == FDFD_PRECOND_MG) {
     MGParams mp = mg_params_from(P->opts);
-    if (P->opts.mg_precision == FDFD_MG_F64) { P->mgd = new Multigrid<double>(); st = P->mgd->setup(ctx, P->op, mp); P->mgd->done = &P->scal.p->done; }
-    else { P->mgf = new Multigrid<float>(); st = P->mgf->setup(ctx, P->op, mp); P->mgf->done = &P->scal.p->done; }
+    if (P->opts.mg_precision == FDFD_MG_F64) { P->mgd = new Multigrid<double>(); st = P->mgd->setup(ctx, P->op, mp); P->mgd->done = &P->w.scal.p->done; }
+    else { P->mgf = new Multigrid<float>(); st = P->mgf->setup(ctx, P->op, mp); P->mgf->done = &P->w.scal.p->done; }
     if (st != FDFD_OK) return fail(st);
   }
   if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { fdfd_set_error(ctx, "setup failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(FDFD_ERR_CUDA); }
@@ -96,7 +87,7 @@ extern "C" int fdfd_problem_set_rhs(fdfd_problem* P, const fdfd_c128* b) {
   if (!P) return FDFD_ERR_ARG;
   ARG_CHECK(P->ctx, b != nullptr, "b is NULL");
   const int64_t N = P->op.g.Nx * P->op.g.Ny;
-  FDFD_TRY(fdfd_copy_in(P->ctx, P->b.p, b, N * sizeof(c128)));
+  FDFD_TRY(fdfd_copy_in(P->ctx, P->w.b.p, b, N * sizeof(c128)));
   CUDA_TRY(P->ctx, cudaStreamSynchronize(P->ctx->stream));
   P->have_rhs = true;
   return FDFD_OK;
@@ -108,8 +99,8 @@ extern "C" int fdfd_problem_set_source(fdfd_problem* P, const fdfd_c128* src) {
   ARG_CHECK(ctx, src != nullptr, "src is NULL");
   const int64_t N = P->op.g.Nx * P->op.g.Ny;
   // stage src in t (scratch), b = 1im*ω*src (driven.jl:36)
-  FDFD_TRY(fdfd_copy_in(ctx, P->t.p, src, N * sizeof(c128)));
-  k_scale_src<<<P->nvec_blocks, 256, 0, ctx->stream>>>(N, c128(0.0, P->op.omega), P->t.p, P->b.p); KLAUNCH(ctx);
+  FDFD_TRY(fdfd_copy_in(ctx, P->w.t.p, src, N * sizeof(c128)));
+  k_scale_src<<<P->w.nvec_blocks, 256, 0, ctx->stream>>>(N, c128(0.0, P->op.omega), P->w.t.p, P->w.b.p); KLAUNCH(ctx);
   CUDA_TRY(ctx, cudaGetLastError());
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   P->have_rhs = true;
@@ -124,7 +115,10 @@ extern "C" int fdfd_problem_solve(fdfd_problem* P, fdfd_info_t* info) {
   std::memset(info, 0, sizeof(*info));
   CUDA_TRY(P->ctx, cudaSetDevice(P->ctx->device));
   const double t0 = now_ms();
-  FDFD_TRY(problem_solve_bicgstab(P, info));
+  KrylovOps ops = P->make_ops();
+  FDFD_TRY(krylov_bicgstab(P->ctx, P->w, ops, P->opts, info));
+  info->setup_ms = P->setup_ms;
+  info->mg_levels = P->mgf ? P->mgf->levels() : (P->mgd ? P->mgd->levels() : 0);
   info->total_ms = now_ms() - t0;
   if (info->flag != FDFD_OK) fdfd_set_error(P->ctx, "Krylov solver stopped with flag %d after %d iterations, relres %.3e", info->flag, info->iters, info->relres);
   return FDFD_OK;  // convergence state is reported through info->flag; results are valid approximations
@@ -134,7 +128,7 @@ extern "C" int fdfd_problem_get_solution(fdfd_problem* P, fdfd_c128* x) {
   if (!P) return FDFD_ERR_ARG;
   ARG_CHECK(P->ctx, x != nullptr, "x is NULL");
   const int64_t N = P->op.g.Nx * P->op.g.Ny;
-  FDFD_TRY(fdfd_copy_out(P->ctx, x, P->x.p, N * sizeof(c128)));
+  FDFD_TRY(fdfd_copy_out(P->ctx, x, P->w.x.p, N * sizeof(c128)));
   CUDA_TRY(P->ctx, cudaStreamSynchronize(P->ctx->stream));
   return FDFD_OK;
 }
@@ -146,7 +140,7 @@ extern "C" int fdfd_problem_get_fields(fdfd_problem* P, int forward_h, fdfd_c128
   const int64_t N = P->op.g.Nx * P->op.g.Ny;
   DevBuf<c128> f3;
   CUDA_TRY(ctx, f3.alloc(3 * N));
-  FDFD_TRY(launch_recover(ctx, P->op, P->x.p, forward_h, std::complex<double>(P->op.omega, 0.0), 0, f3.p));
+  FDFD_TRY(launch_recover(ctx, P->op, P->w.x.p, forward_h, std::complex<double>(P->op.omega, 0.0), 0, f3.p));
   FDFD_TRY(fdfd_copy_out(ctx, fields, f3.p, 3 * N * sizeof(c128)));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return FDFD_OK;
@@ -158,16 +152,16 @@ extern "C" int fdfd_problem_bench_apply(fdfd_problem* P, int nrep, double* ms_pe
   ARG_CHECK(ctx, nrep > 0 && ms_per_apply, "bad arguments");
   const int64_t N = P->op.g.Nx * P->op.g.Ny;
   const bool te = P->op.pol == FDFD_TE;
-  k_fill_random<<<P->nvec_blocks, 256, 0, ctx->stream>>>(N, P->p.p, 1234); KLAUNCH(ctx);
+  k_fill_random<<<P->w.nvec_blocks, 256, 0, ctx->stream>>>(N, P->w.p.p, 1234); KLAUNCH(ctx);
   DotSpec ds;
-  for (int w = 0; w < 3; ++w) FDFD_TRY(launch_apply(ctx, P->op.view(), te, P->p.p, false, P->v.p, ds));
+  for (int w = 0; w < 3; ++w) FDFD_TRY(launch_apply(ctx, P->op.view(), te, P->w.p.p, false, P->w.v.p, ds));
   cudaEvent_t e0, e1;
   CUDA_TRY(ctx, cudaEventCreate(&e0)); CUDA_TRY(ctx, cudaEventCreate(&e1));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
   for (int i = 0; i < nrep; ++i) {
     // ping-pong so consecutive launches do not hit identical cache state
-    FDFD_TRY(launch_apply(ctx, P->op.view(), te, (i & 1) ? P->v.p : P->p.p, false, (i & 1) ? P->p.p : P->v.p, ds));
+    FDFD_TRY(launch_apply(ctx, P->op.view(), te, (i & 1) ? P->w.v.p : P->w.p.p, false, (i & 1) ? P->w.p.p : P->w.v.p, ds));
   }
   CUDA_TRY(ctx, cudaEventRecord(e1, ctx->stream));
   CUDA_TRY(ctx, cudaEventSynchronize(e1));
@@ -183,27 +177,27 @@ extern "C" int fdfd_problem_precond(fdfd_problem* P, const fdfd_c128* in, fdfd_c
   ARG_CHECK(ctx, in && out, "NULL argument");
   ARG_CHECK(ctx, P->mgf || P->mgd, "problem has no multigrid preconditioner");
   const int64_t N = P->op.g.Nx * P->op.g.Ny;
-  FDFD_TRY(fdfd_copy_in(ctx, P->t.p, in, N * sizeof(c128)));
-  const int blocks = P->nvec_blocks;
+  FDFD_TRY(fdfd_copy_in(ctx, P->w.t.p, in, N * sizeof(c128)));
+  const int blocks = P->w.nvec_blocks;
   if (P->mgf) {
     const int* saved = P->mgf->done; P->mgf->done = nullptr;
-    k_cast_in<float><<<blocks, 256, 0, ctx->stream>>>(N, P->t.p, P->mgf->rhs()); KLAUNCH(ctx);
+    k_cast_in<float><<<blocks, 256, 0, ctx->stream>>>(N, P->w.t.p, P->mgf->rhs(), P->mgf->rhs_scale); KLAUNCH(ctx);
     const c64* res = nullptr;
     int st = P->mgf->apply(&res);
     P->mgf->done = saved;
     FDFD_TRY(st);
-    k_cast_out<float><<<blocks, 256, 0, ctx->stream>>>(N, res, P->t.p); KLAUNCH(ctx);
+    k_cast_out<float><<<blocks, 256, 0, ctx->stream>>>(N, res, P->w.t.p); KLAUNCH(ctx);
   } else {
     const int* saved = P->mgd->done; P->mgd->done = nullptr;
-    k_cast_in<double><<<blocks, 256, 0, ctx->stream>>>(N, P->t.p, P->mgd->rhs()); KLAUNCH(ctx);
+    k_cast_in<double><<<blocks, 256, 0, ctx->stream>>>(N, P->w.t.p, P->mgd->rhs(), P->mgd->rhs_scale); KLAUNCH(ctx);
     const c128* res = nullptr;
     int st = P->mgd->apply(&res);
     P->mgd->done = saved;
     FDFD_TRY(st);
-    k_cast_out<double><<<blocks, 256, 0, ctx->stream>>>(N, res, P->t.p); KLAUNCH(ctx);
+    k_cast_out<double><<<blocks, 256, 0, ctx->stream>>>(N, res, P->w.t.p); KLAUNCH(ctx);
   }
   CUDA_TRY(ctx, cudaGetLastError());
-  FDFD_TRY(fdfd_copy_out(ctx, out, P->t.p, N * sizeof(c128)));
+  FDFD_TRY(fdfd_copy_out(ctx, out, P->w.t.p, N * sizeof(c128)));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return FDFD_OK;
 }

@@ -93,13 +93,15 @@ struct fdfd_ctx {
 template <typename T> struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
+  bool own = true;  // false: p aliases memory owned elsewhere
   DevBuf() {}
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
-  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
-  DevBuf& operator=(DevBuf&& o) noexcept { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; return *this; }
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), own(o.own) { o.p = nullptr; o.n = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept { release(); p = o.p; n = o.n; own = o.own; o.p = nullptr; o.n = 0; return *this; }
   ~DevBuf() { release(); }
-  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void release() { if (p && own) cudaFree(p); p = nullptr; n = 0; own = true; }
+  void alias(T* q, size_t count) { release(); p = q; n = count; own = false; }
   cudaError_t alloc(size_t count) {
     release();
     if (count == 0) return cudaSuccess;

@@ -78,6 +78,9 @@ extern "C" void fdfd_default_opts(fdfd_solve_opts_t* o) {
   o->mg_wline = 0.7;
   o->check_every = 8;
   o->verbose = 0;
+  o->mg_shift_growth = 0.0;
+  o->mg_max_levels = 32;
+  o->use_graph = 1;
 }
 
 static bool is_device_ptr(const void* p) {

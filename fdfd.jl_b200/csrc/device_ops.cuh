@@ -18,7 +18,8 @@ template <typename T> struct OpView {
 struct FineOp {
   fdfd_grid_t g{};
   int pol = FDFD_TM, ordering = FDFD_ORDER_FB;
-  double omega = 0;
+  double omega = 0;      // frequency of the mass term
+  double omega_pml = 0;  // frequency the PML s-factors are evaluated at (== omega except modulation.jl:79 sharedpml)
   DevBuf<c128> c1d;    // cxm | cxp | cym | cyp
   DevBuf<c128> mass;   // TM: w^2 eps0 L0 eps_r
   DevBuf<c128> gx, gy; // TE: 1 / grid_average(eps0 L0 eps_r, x|y)
@@ -26,7 +27,8 @@ struct FineOp {
   c128 mass_const{0.0, 0.0};
   Coef1D hc;           // host copy of the 1-D coefficients
 
-  int build(fdfd_ctx* ctx, const fdfd_grid_t& g, int pol, int ordering, double omega, const fdfd_c128* eps_r_any);
+  int build(fdfd_ctx* ctx, const fdfd_grid_t& g, int pol, int ordering, double omega, const fdfd_c128* eps_r_any,
+            double omega_pml = 0.0);
   OpView<double> view() const {
     OpView<double> v;
     v.nx = g.Nx; v.ny = g.Ny;
@@ -39,8 +41,11 @@ struct FineOp {
 // ---- launch wrappers implemented in stencil.cu ------------------------------------------------
 // y = A x.  TI = element type of x (c128 or c64), y is c128.  Optional fused dots (deterministic two-stage):
 //   ndot = 0: none;  1: partial[0] = <d0, y>;  2: partial[0] = <y, d0>, partial[1] = <y, y>   (conjugate-linear in 1st arg)
+// sideband coupling of the modulated operator (modulation.jl:95-101): y += hw * (conj(deps) x_{j+1} + deps x_{j-1})
+struct Coupling { const void* xm1 = nullptr; const void* xp1 = nullptr; const c128* deps = nullptr; double hw = 0.0; };
 struct DotSpec { int ndot = 0; const c128* d0 = nullptr; c128* partials = nullptr; int* nblocks_out = nullptr; const int* done = nullptr; };
-int launch_apply(fdfd_ctx* ctx, const OpView<double>& op, bool te, const void* x, bool x_is_f32, c128* y, const DotSpec& ds);
+int launch_apply(fdfd_ctx* ctx, const OpView<double>& op, bool te, const void* x, bool x_is_f32, c128* y, const DotSpec& ds,
+                 const Coupling* cpl = nullptr);
 
 // H/E recovery written straight into the (Nx,Ny,3) output (K9).  mode: see stencil.cu
 int launch_recover(fdfd_ctx* ctx, const FineOp& op, const c128* u, int forward, std::complex<double> omega_field,

@@ -59,26 +59,26 @@ __global__ void k_scal_init(const c128* __restrict__ partials, int nb, KScal* sc
 template <typename TP>
 __global__ void __launch_bounds__(kVecThreads)
 k_p_update(int64_t N, const KScal* __restrict__ sc, const c128* __restrict__ r, c128* __restrict__ p,
-           const c128* __restrict__ v, TP* __restrict__ pf) {
+           const c128* __restrict__ v, TP* __restrict__ pf, double fscale) {
   if (sc->done) return;
   const c128 beta = sc->beta, omega = sc->omega;
   for (int64_t i = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; i < N; i += (int64_t)gridDim.x * kVecThreads) {
     const c128 pn = r[i] + beta * (p[i] - omega * v[i]);
     p[i] = pn;
-    if (pf) pf[i] = TP(pn);
+    if (pf) pf[i] = TP(c128(fscale * pn.x, fscale * pn.y));
   }
 }
 
 template <typename TP>
 __global__ void __launch_bounds__(kVecThreads)
 k_s_update(int64_t N, const KScal* __restrict__ sc, const c128* __restrict__ r, const c128* __restrict__ v,
-           c128* __restrict__ s, TP* __restrict__ sf) {
+           c128* __restrict__ s, TP* __restrict__ sf, double fscale) {
   if (sc->done) return;
   const c128 alpha = sc->alpha;
   for (int64_t i = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; i < N; i += (int64_t)gridDim.x * kVecThreads) {
     const c128 sn = r[i] - alpha * v[i];
     s[i] = sn;
-    if (sf) sf[i] = TP(sn);
+    if (sf) sf[i] = TP(c128(fscale * sn.x, fscale * sn.y));
   }
 }
 
@@ -172,123 +172,143 @@ __global__ void k_jacobi(OpView<double> op, const c128* __restrict__ in, c128* _
 
 }  // namespace
 
-fdfd_problem::~fdfd_problem() {
-  delete mgf; delete mgd;
+int vec_blocks_for(fdfd_ctx* ctx, int64_t n) { return (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->num_sms * 8); }
+
+int KrylovWork::alloc(fdfd_ctx* ctx, int64_t n_, int nparts, int maxit, bool jacobi_bufs) {
+  n = n_;
+  nvec_blocks = vec_blocks_for(ctx, n);
+  nparts = std::max(nparts, nvec_blocks);
+#define WALLOC(buf, cnt) do { if ((buf).alloc(cnt) != cudaSuccess) { cudaGetLastError(); fdfd_set_error(ctx, "out of device memory allocating %zu elements", (size_t)(cnt)); return FDFD_ERR_ALLOC; } } while (0)
+  WALLOC(b, n); WALLOC(x, n); WALLOC(r, n); WALLOC(rhat, n); WALLOC(p, n); WALLOC(v, n); WALLOC(s, n); WALLOC(t, n);
+  if (jacobi_bufs) { WALLOC(ph, n); WALLOC(sh, n); }
+  WALLOC(partials, (size_t)nparts * 2);
+  WALLOC(scal, 1);
+  WALLOC(hist, (size_t)std::max(16, maxit + 2));
+#undef WALLOC
+  if (cudaMallocHost((void**)&h_scal, sizeof(KScal)) != cudaSuccess) { fdfd_set_error(ctx, "cudaMallocHost failed"); return FDFD_ERR_ALLOC; }
+  return FDFD_OK;
+}
+
+KrylovWork::~KrylovWork() {
+  for (auto& kv : graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   if (h_scal) cudaFreeHost(h_scal);
 }
 
-// one preconditioner application: in-vector was already written (in TP precision) into the MG rhs by the update
-// kernel; returns pointer to the result
-template <typename T>
-static int mg_apply(Multigrid<T>* mg, bool hold, const cplx<T>** out) {
-  FDFD_TRY(mg->apply(out));
-  if (hold) {  // park the result in `spare` so the next cycle does not overwrite it
-    std::swap(mg->lv[0].u.p, mg->spare.p);
-    *out = mg->spare.p;
-  }
+fdfd_problem::~fdfd_problem() { delete mgf; delete mgd; }
+
+int jacobi_apply(fdfd_ctx* ctx, const FineOp& op, const c128* in, c128* out, const int* done, int blocks) {
+  // KScal::done sits at a fixed offset; the kernel takes the KScal pointer
+  const KScal* sc = reinterpret_cast<const KScal*>(reinterpret_cast<const char*>(done) - offsetof(KScal, done));
+  if (op.pol == FDFD_TE) k_jacobi<true><<<blocks, 256, 0, ctx->stream>>>(op.view(), in, out, sc);
+  else k_jacobi<false><<<blocks, 256, 0, ctx->stream>>>(op.view(), in, out, sc);
+  KLAUNCH(ctx);
   return FDFD_OK;
 }
 
 template <typename TP>
-static int bicgstab_loop(fdfd_problem* P, fdfd_info_t* info, TP* mg_rhs, int (*prec)(fdfd_problem*, bool, const TP**)) {
-  fdfd_ctx* ctx = P->ctx;
+static int bicgstab_loop(fdfd_ctx* ctx, KrylovWork& W, const KrylovOps& ops, const fdfd_solve_opts_t& o, fdfd_info_t* info) {
   cudaStream_t st = ctx->stream;
-  const int64_t N = P->op.g.Nx * P->op.g.Ny;
-  const bool te = P->op.pol == FDFD_TE;
-  const OpView<double> A = P->op.view();
-  const int nvb = P->nvec_blocks;
-  const int nab = apply_num_blocks(A.nx, A.ny);
-  const fdfd_solve_opts_t& o = P->opts;
+  const int64_t N = W.n;
+  const int nvb = W.nvec_blocks;
+  const int nab = ops.nab;
   const int check_every = std::max(1, o.check_every);
-  const int hist_len = (int)P->hist.n;
-  KScal* sc = P->scal.p;
-  const bool mgp = o.precond == FDFD_PRECOND_MG;
+  const int hist_len = (int)W.hist.n;
+  KScal* sc = W.scal.p;
+  TP* prhs = (TP*)ops.prec_rhs;
+  const double fscale = ops.fscale;
+  const bool use_graph = o.use_graph && st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
 
-  k_init<<<nvb, kVecThreads, 0, st>>>(N, P->b.p, P->x.p, P->r.p, P->rhat.p, P->p.p, P->v.p, P->partials.p); KLAUNCH(ctx);
-  k_scal_init<<<1, kVecThreads, 0, st>>>(P->partials.p, nvb, sc, o.tol, 0); KLAUNCH(ctx);
+  k_init<<<nvb, kVecThreads, 0, st>>>(N, W.b.p, W.x.p, W.r.p, W.rhat.p, W.p.p, W.v.p, W.partials.p); KLAUNCH(ctx);
+  k_scal_init<<<1, kVecThreads, 0, st>>>(W.partials.p, nvb, sc, o.tol, 0); KLAUNCH(ctx);
   CUDA_TRY(ctx, cudaGetLastError());
 
   int restarts = 0, flag = FDFD_OK;
   int it_enq = 0;
   double true_rel = 0.0;
   while (true) {
-    // ---- enqueue a chunk of iterations
+    // ---- enqueue a chunk of iterations.  One iteration is a fixed kernel sequence (~100-250 launches, most of
+    // them latency-bound coarse-level kernels), so it is captured once per buffer-rotation state into a CUDA
+    // graph and replayed; the rotation (u/tmp ping-pong, spare) has a period of at most 6 iterations.
     for (int c = 0; c < check_every && it_enq < o.maxit; ++c, ++it_enq) {
-      const TP* ph = nullptr; const TP* sh = nullptr;
-      k_p_update<TP><<<nvb, kVecThreads, 0, st>>>(N, sc, P->r.p, P->p.p, P->v.p, mgp ? mg_rhs : (TP*)nullptr); KLAUNCH(ctx);
-      FDFD_TRY(prec(P, true, &ph));
-      DotSpec d1; d1.ndot = 1; d1.d0 = P->rhat.p; d1.partials = P->partials.p; d1.done = &sc->done;
-      FDFD_TRY(launch_apply(ctx, A, te, ph, sizeof(TP) == sizeof(c64), P->v.p, d1));
-      k_scal_alpha<<<1, kVecThreads, 0, st>>>(P->partials.p, nab, sc); KLAUNCH(ctx);
-      k_s_update<TP><<<nvb, kVecThreads, 0, st>>>(N, sc, P->r.p, P->v.p, P->s.p, mgp ? mg_rhs : (TP*)nullptr); KLAUNCH(ctx);
-      FDFD_TRY(prec(P, false, &sh));
-      DotSpec d2; d2.ndot = 2; d2.d0 = P->s.p; d2.partials = P->partials.p; d2.done = &sc->done;
-      FDFD_TRY(launch_apply(ctx, A, te, sh, sizeof(TP) == sizeof(c64), P->t.p, d2));
-      k_scal_omega<<<1, kVecThreads, 0, st>>>(P->partials.p, nab, sc); KLAUNCH(ctx);
-      k_xr_update<TP><<<nvb, kVecThreads, 0, st>>>(N, sc, P->x.p, ph, sh, P->s.p, P->t.p, P->r.p, P->rhat.p, P->partials.p); KLAUNCH(ctx);
-      k_scal_rho<<<1, kVecThreads, 0, st>>>(P->partials.p, nvb, sc, P->hist.p, hist_len); KLAUNCH(ctx);
+      auto one_iteration = [&]() -> int {
+        const void* ph = nullptr; const void* sh = nullptr;
+        k_p_update<TP><<<nvb, kVecThreads, 0, st>>>(N, sc, W.r.p, W.p.p, W.v.p, prhs, fscale); KLAUNCH(ctx);
+        FDFD_TRY(ops.precond(true, &ph));
+        DotSpec d1; d1.ndot = 1; d1.d0 = W.rhat.p; d1.partials = W.partials.p; d1.done = &sc->done;
+        FDFD_TRY(ops.apply(ph, sizeof(TP) == sizeof(c64), W.v.p, d1));
+        k_scal_alpha<<<1, kVecThreads, 0, st>>>(W.partials.p, nab, sc); KLAUNCH(ctx);
+        k_s_update<TP><<<nvb, kVecThreads, 0, st>>>(N, sc, W.r.p, W.v.p, W.s.p, prhs, fscale); KLAUNCH(ctx);
+        FDFD_TRY(ops.precond(false, &sh));
+        DotSpec d2; d2.ndot = 2; d2.d0 = W.s.p; d2.partials = W.partials.p; d2.done = &sc->done;
+        FDFD_TRY(ops.apply(sh, sizeof(TP) == sizeof(c64), W.t.p, d2));
+        k_scal_omega<<<1, kVecThreads, 0, st>>>(W.partials.p, nab, sc); KLAUNCH(ctx);
+        k_xr_update<TP><<<nvb, kVecThreads, 0, st>>>(N, sc, W.x.p, (const TP*)ph, (const TP*)sh, W.s.p, W.t.p, W.r.p, W.rhat.p, W.partials.p); KLAUNCH(ctx);
+        k_scal_rho<<<1, kVecThreads, 0, st>>>(W.partials.p, nvb, sc, W.hist.p, hist_len); KLAUNCH(ctx);
+        return FDFD_OK;
+      };
+      if (!use_graph) { FDFD_TRY(one_iteration()); continue; }
+      std::vector<void*> key;
+      if (ops.get_state) ops.get_state(key);
+      auto itg = W.graphs.find(key);
+      if (itg == W.graphs.end()) {
+        const int64_t l0 = ctx->launches;
+        CUDA_TRY(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+        int rc = one_iteration();
+        cudaGraph_t graph = nullptr;
+        cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        if (rc != FDFD_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+        CUDA_TRY(ctx, ce);
+        IterGraph ig;
+        ig.nlaunch = ctx->launches - l0;
+        ctx->launches = l0;
+        CUDA_TRY(ctx, cudaGraphInstantiate(&ig.exec, graph, 0));
+        cudaGraphDestroy(graph);
+        if (ops.get_state) ops.get_state(ig.post);
+        itg = W.graphs.emplace(key, ig).first;
+      } else if (ops.set_state) {
+        ops.set_state(itg->second.post);
+      }
+      CUDA_TRY(ctx, cudaGraphLaunch(itg->second.exec, st));
+      ctx->launches += itg->second.nlaunch;
     }
     CUDA_TRY(ctx, cudaGetLastError());
-    CUDA_TRY(ctx, cudaMemcpyAsync(P->h_scal, sc, sizeof(KScal), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(W.h_scal, sc, sizeof(KScal), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    const KScal h = *P->h_scal;
+    const KScal h = *W.h_scal;
     if (o.verbose) fprintf(stderr, "[fdfd_b200] it %d relres %.3e%s\n", h.iter, std::sqrt(h.rr / h.bnorm2), h.breakdown ? " (breakdown)" : "");
     const bool out_of_its = it_enq >= o.maxit;
     if (!h.done && !out_of_its) continue;
     if (h.bnorm2 == 0.0) { true_rel = 0.0; break; }  // b = 0 -> x = 0
     // ---- true residual with the fp64 operator
     DotSpec d0;
-    FDFD_TRY(launch_apply(ctx, A, te, P->x.p, false, P->t.p, d0));
-    k_true_resid<<<nvb, kVecThreads, 0, st>>>(N, P->b.p, P->t.p, P->partials.p); KLAUNCH(ctx);
-    k_scal_init<<<1, kVecThreads, 0, st>>>(P->partials.p, nvb, sc, o.tol, 2); KLAUNCH(ctx);
-    CUDA_TRY(ctx, cudaMemcpyAsync(P->h_scal, sc, sizeof(KScal), cudaMemcpyDeviceToHost, st));
+    FDFD_TRY(ops.apply(W.x.p, false, W.t.p, d0));
+    k_true_resid<<<nvb, kVecThreads, 0, st>>>(N, W.b.p, W.t.p, W.partials.p); KLAUNCH(ctx);
+    k_scal_init<<<1, kVecThreads, 0, st>>>(W.partials.p, nvb, sc, o.tol, 2); KLAUNCH(ctx);
+    CUDA_TRY(ctx, cudaMemcpyAsync(W.h_scal, sc, sizeof(KScal), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    true_rel = std::sqrt(P->h_scal->rr / P->h_scal->bnorm2);
+    true_rel = std::sqrt(W.h_scal->rr / W.h_scal->bnorm2);
     if (std::isfinite(true_rel) && true_rel <= o.tol) { flag = FDFD_OK; break; }
     if (out_of_its) { flag = FDFD_ERR_NOCONV; break; }
     if (restarts >= 8) { flag = h.breakdown ? FDFD_ERR_BREAKDOWN : FDFD_ERR_NOCONV; break; }
     if (!std::isfinite(true_rel)) { flag = FDFD_ERR_BREAKDOWN; break; }
     // ---- restart from the current x (cures breakdown and recurrence drift)
     ++restarts;
-    k_restart<<<nvb, kVecThreads, 0, st>>>(N, P->b.p, P->t.p, P->r.p, P->rhat.p, P->p.p, P->v.p, P->partials.p); KLAUNCH(ctx);
-    k_scal_init<<<1, kVecThreads, 0, st>>>(P->partials.p, nvb, sc, o.tol, 1); KLAUNCH(ctx);
+    k_restart<<<nvb, kVecThreads, 0, st>>>(N, W.b.p, W.t.p, W.r.p, W.rhat.p, W.p.p, W.v.p, W.partials.p); KLAUNCH(ctx);
+    k_scal_init<<<1, kVecThreads, 0, st>>>(W.partials.p, nvb, sc, o.tol, 1); KLAUNCH(ctx);
   }
-  info->iters = P->h_scal->iter;
+  info->iters = W.h_scal->iter;
   info->relres = true_rel;
   info->flag = flag;
   info->restarts = restarts;
   return FDFD_OK;
 }
 
-static int prec_mg32(fdfd_problem* P, bool hold, const c64** out) { return mg_apply<float>(P->mgf, hold, out); }
-static int prec_mg64(fdfd_problem* P, bool hold, const c128** out) { return mg_apply<double>(P->mgd, hold, out); }
-static int prec_none(fdfd_problem* P, bool hold, const c128** out) { *out = hold ? P->p.p : P->s.p; return FDFD_OK; }
-static int prec_jacobi(fdfd_problem* P, bool hold, const c128** out) {
-  c128* dst = hold ? P->ph.p : P->sh.p;
-  const c128* src = hold ? P->p.p : P->s.p;
-  const int blocks = P->nvec_blocks;
-  if (P->op.pol == FDFD_TE) k_jacobi<true><<<blocks, 256, 0, P->ctx->stream>>>(P->op.view(), src, dst, P->scal.p);
-  else k_jacobi<false><<<blocks, 256, 0, P->ctx->stream>>>(P->op.view(), src, dst, P->scal.p);
-  P->ctx->launches++;
-  *out = dst;
-  return FDFD_OK;
-}
-
-int problem_solve_bicgstab(fdfd_problem* P, fdfd_info_t* info) {
-  fdfd_ctx* ctx = P->ctx;
+int krylov_bicgstab(fdfd_ctx* ctx, KrylovWork& W, const KrylovOps& ops, const fdfd_solve_opts_t& o, fdfd_info_t* info) {
   cudaEvent_t e0, e1;
   CUDA_TRY(ctx, cudaEventCreate(&e0)); CUDA_TRY(ctx, cudaEventCreate(&e1));
   const int64_t l0 = ctx->launches;
   CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
-  int st;
-  if (P->opts.precond == FDFD_PRECOND_MG) {
-    if (P->mgf) st = bicgstab_loop<c64>(P, info, P->mgf->rhs(), prec_mg32);
-    else st = bicgstab_loop<c128>(P, info, P->mgd->rhs(), prec_mg64);
-  } else if (P->opts.precond == FDFD_PRECOND_JACOBI) {
-    st = bicgstab_loop<c128>(P, info, nullptr, prec_jacobi);
-  } else {
-    st = bicgstab_loop<c128>(P, info, nullptr, prec_none);
-  }
+  int st = ops.prec_f32 ? bicgstab_loop<c64>(ctx, W, ops, o, info) : bicgstab_loop<c128>(ctx, W, ops, o, info);
   cudaEventRecord(e1, ctx->stream);
   cudaEventSynchronize(e1);
   float ms = 0;
@@ -296,8 +316,56 @@ int problem_solve_bicgstab(fdfd_problem* P, fdfd_info_t* info) {
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   info->solve_ms = ms;
   info->launches = ctx->launches - l0;
-  info->setup_ms = P->setup_ms;
-  info->mg_levels = P->mgf ? P->mgf->levels() : (P->mgd ? P->mgd->levels() : 0);
-  P->have_x = (st == FDFD_OK);
   return st;
+}
+
+// ---- the single-operator problem (driven TM / TE) -------------------------------------------------------
+template <typename T> static void mg_get_state(Multigrid<T>* mg, std::vector<void*>& v) {
+  for (auto& L : mg->lv) { v.push_back(L.u.p); v.push_back(L.tmp.p); }
+  v.push_back(mg->spare.p);
+}
+template <typename T> static void mg_set_state(Multigrid<T>* mg, const std::vector<void*>& v, size_t& k) {
+  for (auto& L : mg->lv) { L.u.p = (cplx<T>*)v[k++]; L.tmp.p = (cplx<T>*)v[k++]; }
+  mg->spare.p = (cplx<T>*)v[k++];
+}
+// one preconditioner application: the input was already written (scaled, in T precision) into the MG rhs
+template <typename T> static int mg_apply_hold(Multigrid<T>* mg, bool hold, const void** out) {
+  const cplx<T>* res = nullptr;
+  FDFD_TRY(mg->apply(&res));
+  if (hold) {  // park the result in `spare` so the next cycle does not overwrite it
+    std::swap(mg->lv[0].u.p, mg->spare.p);
+    res = mg->spare.p;
+  }
+  *out = res;
+  return FDFD_OK;
+}
+
+KrylovOps fdfd_problem::make_ops() {
+  KrylovOps k;
+  fdfd_problem* P = this;
+  const bool te = op.pol == FDFD_TE;
+  k.nab = apply_num_blocks(op.g.Nx, op.g.Ny);
+  k.apply = [P, te](const void* x, bool x_f32, c128* y, const DotSpec& ds) { return launch_apply(P->ctx, P->op.view(), te, x, x_f32, y, ds); };
+  if (opts.precond == FDFD_PRECOND_MG && mgf) {
+    k.prec_f32 = true; k.prec_rhs = mgf->rhs(); k.fscale = mgf->rhs_scale;
+    k.precond = [P](bool hold, const void** out) { return mg_apply_hold<float>(P->mgf, hold, out); };
+    k.get_state = [P](std::vector<void*>& v) { v.clear(); mg_get_state(P->mgf, v); };
+    k.set_state = [P](const std::vector<void*>& v) { size_t i = 0; mg_set_state(P->mgf, v, i); };
+  } else if (opts.precond == FDFD_PRECOND_MG && mgd) {
+    k.prec_f32 = false; k.prec_rhs = mgd->rhs(); k.fscale = mgd->rhs_scale;
+    k.precond = [P](bool hold, const void** out) { return mg_apply_hold<double>(P->mgd, hold, out); };
+    k.get_state = [P](std::vector<void*>& v) { v.clear(); mg_get_state(P->mgd, v); };
+    k.set_state = [P](const std::vector<void*>& v) { size_t i = 0; mg_set_state(P->mgd, v, i); };
+  } else if (opts.precond == FDFD_PRECOND_JACOBI) {
+    k.prec_f32 = false;
+    k.precond = [P](bool hold, const void** out) {
+      c128* dst = hold ? P->w.ph.p : P->w.sh.p;
+      *out = dst;
+      return jacobi_apply(P->ctx, P->op, hold ? P->w.p.p : P->w.s.p, dst, &P->w.scal.p->done, P->w.nvec_blocks);
+    };
+  } else {
+    k.prec_f32 = false;
+    k.precond = [P](bool hold, const void** out) { *out = hold ? P->w.p.p : P->w.s.p; return FDFD_OK; };
+  }
+  return k;
 }

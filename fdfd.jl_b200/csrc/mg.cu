@@ -49,13 +49,15 @@ __device__ __forceinline__ int64_t strip_index(int64_t c, int64_t n, int np) { r
 // TM: mass = (1 - i beta) w^2 eps0 eps ;  TE: gx, gy = 1/grid_average(eps0 eps)
 template <typename T, bool TE>
 __global__ void k_level_setup(int64_t nx, int64_t ny, const c128* __restrict__ eps, double w2eps0, double beta, double eps0,
-                              cplx<T>* __restrict__ mass, cplx<T>* __restrict__ gx, cplx<T>* __restrict__ gy) {
+                              double growth_kfac, cplx<T>* __restrict__ mass, cplx<T>* __restrict__ gx, cplx<T>* __restrict__ gy) {
   const int64_t N = nx * ny;
   for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
     const c128 e = eps[n];
     if (!TE) {
-      // (1 - i beta) * w^2 eps0 * e
-      mass[n] = cplx<T>(T(w2eps0 * (e.x + beta * e.y)), T(w2eps0 * (e.y - beta * e.x)));
+      // (1 - i beta_eff) * w^2 eps0 * e ; beta_eff grows with the local k^2 h_l^2 so that coarse levels whose
+      // re-discretised dispersion is wrong (kh >~ 1) become damped instead of resonant
+      const double be = fmax(beta, growth_kfac * e.x);
+      mass[n] = cplx<T>(T(w2eps0 * (e.x + be * e.y)), T(w2eps0 * (e.y - be * e.x)));
     } else {
       const int64_t ix = n % nx, iy = n / nx;
       const int64_t ixm = ix == 0 ? nx - 1 : ix - 1, iym = iy == 0 ? ny - 1 : iy - 1;
@@ -272,6 +274,8 @@ template <typename T> int Multigrid<T>::setup(fdfd_ctx* ctx_, const FineOp& op, 
   const fdfd_grid_t& g = op.g;
   const double eps0 = kEps0 * g.L0, mu0 = kMu0 * g.L0;
   const double scale = te ? 1.0 : 1.0 / mu0;
+  // store M scaled to O(1) coefficients (TE couplings are ~1e21 in SI-normalised units: |C|^2 overflows fp32)
+  rhs_scale = (te ? eps0 : 1.0) / std::abs(op.hc.cxm[g.Nx / 2]);
   lv.clear();
   // level sizes
   std::vector<std::pair<int64_t, int64_t>> sizes;
@@ -290,9 +294,9 @@ template <typename T> int Multigrid<T>::setup(fdfd_ctx* ctx_, const FineOp& op, 
     const int64_t N = L.nx * L.ny;
     // 1-D coefficients
     Coef1D hc;
-    if (l == 0) hc = op.hc; else host_coef_level(g, op.omega, op.ordering, scale, L.stride, L.nx, L.ny, hc);
+    if (l == 0) hc = op.hc; else host_coef_level(g, op.omega_pml, op.ordering, scale, L.stride, L.nx, L.ny, hc);
     std::vector<cplx<T>> pack; pack.reserve(2 * L.nx + 2 * L.ny);
-    for (auto* v : {&hc.cxm, &hc.cxp, &hc.cym, &hc.cyp}) for (auto& z : *v) pack.push_back(cplx<T>(T(z.real()), T(z.imag())));
+    for (auto* v : {&hc.cxm, &hc.cxp, &hc.cym, &hc.cyp}) for (auto& z : *v) pack.push_back(cplx<T>(T(z.real() * rhs_scale), T(z.imag() * rhs_scale)));
     CUDA_TRY(ctx, L.c1d.alloc(pack.size()));
     CUDA_TRY(ctx, cudaMemcpyAsync(L.c1d.p, pack.data(), pack.size() * sizeof(cplx<T>), cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -312,12 +316,14 @@ template <typename T> int Multigrid<T>::setup(fdfd_ctx* ctx_, const FineOp& op, 
       const int blocks = (int)std::min<int64_t>((N + threads - 1) / threads, (int64_t)ctx->num_sms * 16);
       if (te) {
         CUDA_TRY(ctx, L.gx.alloc(N)); CUDA_TRY(ctx, L.gy.alloc(N));
-        k_level_setup<T, true><<<blocks, threads, 0, ctx->stream>>>(L.nx, L.ny, eps_l, 0.0, prm.beta, eps0, nullptr, L.gx.p, L.gy.p);
-        const double m = op.omega * op.omega * mu0;
+        k_level_setup<T, true><<<blocks, threads, 0, ctx->stream>>>(L.nx, L.ny, eps_l, 0.0, prm.beta, eps0, 0.0, nullptr, L.gx.p, L.gy.p);
+        const double m = op.omega * op.omega * mu0 * rhs_scale;
         L.mass_const = cplx<T>(T(m), T(-prm.beta * m));
       } else {
         CUDA_TRY(ctx, L.mass.alloc(N));
-        k_level_setup<T, false><<<blocks, threads, 0, ctx->stream>>>(L.nx, L.ny, eps_l, op.omega * op.omega * eps0, prm.beta, eps0,
+        const double w2 = op.omega * op.omega * eps0 * rhs_scale;  // ~ k0^2 dx^2
+        k_level_setup<T, false><<<blocks, threads, 0, ctx->stream>>>(L.nx, L.ny, eps_l, w2, prm.beta, eps0,
+                                                                   prm.shift_growth * w2 * (double)(L.stride * L.stride),
                                                                    L.mass.p, nullptr, nullptr);
       }
       KLAUNCH(ctx);

@@ -36,7 +36,7 @@ template <typename T> struct MGLevel {
 
 struct MGParams {
   int cycle = FDFD_CYCLE_W, wdepth = 4, nu1 = 1, nu2 = 1, coarse_sweeps = 4;
-  double beta = 0.5, wjac = 0.8, wline = 0.7;
+  double beta = 0.5, wjac = 0.8, wline = 0.7, shift_growth = 0.0;
   int min_n = 2, pad = 1, max_levels = 32;
 };
 
@@ -48,6 +48,7 @@ template <typename T> struct Multigrid {
   DevBuf<c128> pcr_scratch;   // setup-only scratch
   DevBuf<cplx<T>> line_scratch;  // global ping-pong for lines too long for shared memory
   DevBuf<cplx<T>> spare;         // third level-0 buffer: lets the caller keep one result across the next apply
+  double rhs_scale = 1.0;        // M is stored scaled by this factor (keeps fp32 in range); callers scale the rhs they write
   const int* done = nullptr;     // optional device flag: kernels early-exit once the Krylov loop has converged
 
   // build hierarchy for the operator `op` (fine eps_r resident in op.eps)

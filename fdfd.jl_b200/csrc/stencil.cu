@@ -41,7 +41,8 @@ constexpr int kApplyThreads = 128;
 template <typename TI, bool TE, int NDOT, int ROWS>
 __global__ void __launch_bounds__(kApplyThreads)
 k_apply(OpView<double> op, const TI* __restrict__ x, c128* __restrict__ y, const c128* __restrict__ d0,
-        c128* __restrict__ partials, const int* __restrict__ done) {
+        c128* __restrict__ partials, const int* __restrict__ done, const TI* __restrict__ xm1, const TI* __restrict__ xp1,
+        const c128* __restrict__ deps, double hw) {
   if (done && *done) return;
   const int64_t Nx = op.nx, Ny = op.ny;
   const int64_t ix = blockIdx.x * (int64_t)kApplyThreads + threadIdx.x;
@@ -78,6 +79,13 @@ k_apply(OpView<double> op, const TI* __restrict__ x, c128* __restrict__ y, const
       const c128 C = ((-W - E) + (-S - Nn)) + m;
       c128 out = C * uc;
       cfma(out, W, uw); cfma(out, E, ue); cfma(out, S, us); cfma(out, Nn, un);
+      if (deps) {  // sideband coupling (block-coupled MF-FDFD operator)
+        const c128 de = deps[n];
+        c128 cp(0.0, 0.0);
+        if (xp1) cp += conj(de) * ldx(xp1, n);
+        if (xm1) cp += de * ldx(xm1, n);
+        out += c128(hw * cp.x, hw * cp.y);
+      }
       y[n] = out;
       if constexpr (NDOT == 1) {  // <d0, y> = sum conj(d0) y
         const c128 d = d0[n];
@@ -131,13 +139,14 @@ __global__ void k_recover(int64_t Nx, int64_t Ny, const c128* __restrict__ u, co
 
 }  // namespace
 
-int FineOp::build(fdfd_ctx* ctx, const fdfd_grid_t& g_, int pol_, int ordering_, double omega_, const fdfd_c128* eps_r_any) {
-  g = g_; pol = pol_; ordering = ordering_; omega = omega_;
+int FineOp::build(fdfd_ctx* ctx, const fdfd_grid_t& g_, int pol_, int ordering_, double omega_, const fdfd_c128* eps_r_any,
+                  double omega_pml_) {
+  g = g_; pol = pol_; ordering = ordering_; omega = omega_; omega_pml = omega_pml_ > 0 ? omega_pml_ : omega_;
   const int64_t N = g.Nx * g.Ny;
   ARG_CHECK(ctx, !(pol == FDFD_TE && ordering != FDFD_ORDER_FB), "TE is defined for the f.b ordering only");
   const double eps0 = kEps0 * g.L0, mu0 = kMu0 * g.L0;
   // TM: mu0^-1 folded into the 1-D coefficients (driven.jl:35 `δxf*μ₀^-1*δxb`); TE: none (driven.jl:45)
-  host_coef_fine(g, omega, ordering, pol == FDFD_TM ? 1.0 / mu0 : 1.0, hc);
+  host_coef_fine(g, omega_pml, ordering, pol == FDFD_TM ? 1.0 / mu0 : 1.0, hc);
   CUDA_TRY(ctx, c1d.alloc(2 * g.Nx + 2 * g.Ny));
   std::vector<std::complex<double>> pack;
   pack.insert(pack.end(), hc.cxm.begin(), hc.cxm.end()); pack.insert(pack.end(), hc.cxp.begin(), hc.cxp.end());
@@ -164,11 +173,12 @@ int FineOp::build(fdfd_ctx* ctx, const fdfd_grid_t& g_, int pol_, int ordering_,
 }
 
 template <typename TI, bool TE, int NDOT>
-static int launch_apply_t(fdfd_ctx* ctx, const OpView<double>& op, const TI* x, c128* y, const DotSpec& ds) {
+static int launch_apply_t(fdfd_ctx* ctx, const OpView<double>& op, const TI* x, c128* y, const DotSpec& ds, const Coupling* cpl) {
   constexpr int ROWS = 8;
   dim3 grid((unsigned)((op.nx + kApplyThreads - 1) / kApplyThreads), (unsigned)((op.ny + ROWS - 1) / ROWS));
   if (ds.nblocks_out) *ds.nblocks_out = (int)(grid.x * grid.y);
-  k_apply<TI, TE, NDOT, ROWS><<<grid, kApplyThreads, 0, ctx->stream>>>(op, x, y, ds.d0, ds.partials, ds.done);
+  k_apply<TI, TE, NDOT, ROWS><<<grid, kApplyThreads, 0, ctx->stream>>>(op, x, y, ds.d0, ds.partials, ds.done,
+      cpl ? (const TI*)cpl->xm1 : nullptr, cpl ? (const TI*)cpl->xp1 : nullptr, cpl ? cpl->deps : nullptr, cpl ? cpl->hw : 0.0);
   KLAUNCH(ctx);
   CUDA_TRY(ctx, cudaGetLastError());
   return FDFD_OK;
@@ -178,12 +188,13 @@ int apply_num_blocks(int64_t nx, int64_t ny) {
   return (int)(((nx + kApplyThreads - 1) / kApplyThreads) * ((ny + 8 - 1) / 8));
 }
 
-int launch_apply(fdfd_ctx* ctx, const OpView<double>& op, bool te, const void* x, bool x_is_f32, c128* y, const DotSpec& ds) {
+int launch_apply(fdfd_ctx* ctx, const OpView<double>& op, bool te, const void* x, bool x_is_f32, c128* y, const DotSpec& ds,
+                 const Coupling* cpl) {
 #define DISPATCH(TI, TEV)                                                                        \
   switch (ds.ndot) {                                                                             \
-    case 0: return launch_apply_t<TI, TEV, 0>(ctx, op, (const TI*)x, y, ds);                     \
-    case 1: return launch_apply_t<TI, TEV, 1>(ctx, op, (const TI*)x, y, ds);                     \
-    default: return launch_apply_t<TI, TEV, 2>(ctx, op, (const TI*)x, y, ds);                    \
+    case 0: return launch_apply_t<TI, TEV, 0>(ctx, op, (const TI*)x, y, ds, cpl);                     \
+    case 1: return launch_apply_t<TI, TEV, 1>(ctx, op, (const TI*)x, y, ds, cpl);                     \
+    default: return launch_apply_t<TI, TEV, 2>(ctx, op, (const TI*)x, y, ds, cpl);                    \
   }
   if (x_is_f32) { if (te) { DISPATCH(c64, true) } else { DISPATCH(c64, false) } }
   else          { if (te) { DISPATCH(c128, true) } else { DISPATCH(c128, false) } }
@@ -198,7 +209,7 @@ int launch_recover(fdfd_ctx* ctx, const FineOp& op, const c128* u, int forward, 
   const double mu0 = kMu0 * g.L0;
   // inverse s-factors of the requested difference direction, frozen at the operator's omega
   std::vector<std::complex<double>> sx, sy;
-  host_sfactor(g, 0, forward, op.omega, sx); host_sfactor(g, 1, forward, op.omega, sy);
+  host_sfactor(g, 0, forward, op.omega_pml, sx); host_sfactor(g, 1, forward, op.omega_pml, sy);
   for (auto& z : sx) z = 1.0 / z;
   for (auto& z : sy) z = 1.0 / z;
   DevBuf<c128> ds;

@@ -82,6 +82,9 @@ typedef struct {
   double  mg_wline;      /* PML line-relaxation damping (default 0.7) */
   int32_t check_every;   /* host polls convergence every k iterations (default 8) */
   int32_t verbose;
+  double  mg_shift_growth; /* level/space dependent shift: beta_eff = max(beta, growth * Re(k^2 h_l^2)) (default 0 = off) */
+  int32_t mg_max_levels; /* cap on hierarchy depth (default 32) */
+  int32_t use_graph;     /* replay the iteration as a CUDA graph (default 1) */
 } fdfd_solve_opts_t;
 
 typedef struct {
@@ -173,6 +176,10 @@ int fdfd_problem_get_fields(fdfd_problem* p, int forward_h, fdfd_c128* fields); 
 int fdfd_problem_bench_apply(fdfd_problem* p, int nrep, double* ms_per_apply);
 /* one application of the preconditioner M^-1 to a resident vector (parity/debug hook) */
 int fdfd_problem_precond(fdfd_problem* p, const fdfd_c128* in, fdfd_c128* out);
+
+/* host-only test hook (no GPU needed): the small dense complex Hessenberg eigen-solver behind the Ritz pairs of
+ * fdfd_eigenfrequency.  H, evecs: column-major n x n; evals: n. */
+int fdfd_debug_hess_eig(int n, const fdfd_c128* H, fdfd_c128* evals, fdfd_c128* evecs);
 
 #ifdef __cplusplus
 }

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol(fdfd):
 
 def test_struct_layouts_match_header(fdfd):
     assert ctypes.sizeof(fdfd.GridT) == 4 * 8 + 5 * 8
-    assert ctypes.sizeof(fdfd.SolveOpts) == 80
+    assert ctypes.sizeof(fdfd.SolveOpts) == 96
     assert ctypes.sizeof(fdfd.Info) == 56
     o = fdfd.default_opts()
     assert o.tol == 1e-10 and o.precond == fdfd._lib.PRECOND_MG and o.mg_beta == 0.5
@@ -65,3 +65,17 @@ def test_host_mirror_grid_matches_oracle(fdfd):
     fdfd.add_mode(d, fdfd.Mode(fdfd.TM, fdfd.XHAT, 3.5, fdfd.Point(1.0, 0), 0.8)); do.modes.append(O.Mode(O.TM, O.X, 3.5, (1.0, 0), 0.8))
     fdfd._apply_modes(d, w); O._apply_modes(do, w)
     assert np.allclose(d.src, do.src, rtol=1e-12, atol=1e-15) and abs(np.linalg.norm(d.src) - 1) < 1e-12
+
+
+def test_hessenberg_eigensolver_host(fdfd):
+    """the small dense solver behind fdfd_eigenfrequency's Ritz pairs (host code, no GPU)"""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 7, 40, 120):
+        H = np.triu(rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)), -1)
+        Hf = np.asfortranarray(H); ev = np.empty(n, complex); vec = np.empty((n, n), complex, order="F")
+        assert fdfd.lib().fdfd_debug_hess_eig(n, fdfd.ptr(Hf), fdfd.ptr(ev), fdfd.ptr(vec)) == 0
+        ref = np.linalg.eigvals(H)
+        assert max(min(abs(e - ref)) for e in ev) < 1e-10 * max(1, abs(ref).max())
+        for k in range(n):
+            assert np.linalg.norm(H @ vec[:, k] - ev[k] * vec[:, k]) < 1e-10 * max(1, abs(ref).max())
