@@ -38,8 +38,12 @@ template <typename TI> __device__ __forceinline__ c128 ldx(const TI* p, int64_t 
 
 constexpr int kApplyThreads = 128;
 
-template <typename TI, bool TE, int NDOT, int ROWS>
-__global__ void __launch_bounds__(kApplyThreads)
+// streaming (evict-first) access for operands touched exactly once: the w^2 eps term and the output
+__device__ __forceinline__ c128 ld_stream(const c128* p) { const double2 v = __ldcs(reinterpret_cast<const double2*>(p)); return c128(v.x, v.y); }
+__device__ __forceinline__ void st_stream(c128* p, c128 v) { __stcs(reinterpret_cast<double2*>(p), make_double2(v.x, v.y)); }
+
+template <typename TI, bool TE, int NDOT, int ROWS, int MINB, bool HINT>
+__global__ void __launch_bounds__(kApplyThreads, MINB)
 k_apply(OpView<double> op, const TI* __restrict__ x, c128* __restrict__ y, const c128* __restrict__ d0,
         c128* __restrict__ partials, const int* __restrict__ done, const TI* __restrict__ xm1, const TI* __restrict__ xp1,
         const c128* __restrict__ deps, double hw) {
@@ -73,7 +77,7 @@ k_apply(OpView<double> op, const TI* __restrict__ x, c128* __restrict__ y, const
         gyc = gyn;
         m = op.mass_const;
       } else {
-        m = op.mass[n];
+        m = HINT ? ld_stream(op.mass + n) : op.mass[n];
       }
       // y = W uw + E ue + S us + N un + ((-(W+E) - (S+N)) + m) uc   (same association as the assembled matrix)
       const c128 C = ((-W - E) + (-S - Nn)) + m;
@@ -86,7 +90,7 @@ k_apply(OpView<double> op, const TI* __restrict__ x, c128* __restrict__ y, const
         if (xm1) cp += de * ldx(xm1, n);
         out += c128(hw * cp.x, hw * cp.y);
       }
-      y[n] = out;
+      if (HINT) st_stream(y + n, out); else y[n] = out;
       if constexpr (NDOT == 1) {  // <d0, y> = sum conj(d0) y
         const c128 d = d0[n];
         const c128 p = cmulc(d, out);
@@ -172,20 +176,41 @@ int FineOp::build(fdfd_ctx* ctx, const fdfd_grid_t& g_, int pol_, int ordering_,
   return FDFD_OK;
 }
 
-template <typename TI, bool TE, int NDOT>
-static int launch_apply_t(fdfd_ctx* ctx, const OpView<double>& op, const TI* x, c128* y, const DotSpec& ds, const Coupling* cpl) {
-  constexpr int ROWS = 8;
+// tuning variants (FDFD_APPLY_VARIANT): rows marched per thread, min CTAs/SM (register cap), streaming hints
+static int apply_variant() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FDFD_APPLY_VARIANT"); v = e ? atoi(e) : 0; if (v < 0 || v > 6) v = 0; }
+  return v;
+}
+static int variant_rows(int v) { static const int rows[7] = {8, 8, 16, 4, 8, 16, 32}; return rows[v]; }
+
+template <typename TI, bool TE, int NDOT, int ROWS, int MINB, bool HINT>
+static int launch_apply_v(fdfd_ctx* ctx, const OpView<double>& op, const TI* x, c128* y, const DotSpec& ds, const Coupling* cpl) {
   dim3 grid((unsigned)((op.nx + kApplyThreads - 1) / kApplyThreads), (unsigned)((op.ny + ROWS - 1) / ROWS));
   if (ds.nblocks_out) *ds.nblocks_out = (int)(grid.x * grid.y);
-  k_apply<TI, TE, NDOT, ROWS><<<grid, kApplyThreads, 0, ctx->stream>>>(op, x, y, ds.d0, ds.partials, ds.done,
+  k_apply<TI, TE, NDOT, ROWS, MINB, HINT><<<grid, kApplyThreads, 0, ctx->stream>>>(op, x, y, ds.d0, ds.partials, ds.done,
       cpl ? (const TI*)cpl->xm1 : nullptr, cpl ? (const TI*)cpl->xp1 : nullptr, cpl ? cpl->deps : nullptr, cpl ? cpl->hw : 0.0);
   KLAUNCH(ctx);
   CUDA_TRY(ctx, cudaGetLastError());
   return FDFD_OK;
 }
 
+template <typename TI, bool TE, int NDOT>
+static int launch_apply_t(fdfd_ctx* ctx, const OpView<double>& op, const TI* x, c128* y, const DotSpec& ds, const Coupling* cpl) {
+  switch (apply_variant()) {
+    case 1: return launch_apply_v<TI, TE, NDOT, 8, 8, true>(ctx, op, x, y, ds, cpl);
+    case 2: return launch_apply_v<TI, TE, NDOT, 16, 8, true>(ctx, op, x, y, ds, cpl);
+    case 3: return launch_apply_v<TI, TE, NDOT, 4, 8, true>(ctx, op, x, y, ds, cpl);
+    case 4: return launch_apply_v<TI, TE, NDOT, 8, 1, true>(ctx, op, x, y, ds, cpl);
+    case 5: return launch_apply_v<TI, TE, NDOT, 16, 6, true>(ctx, op, x, y, ds, cpl);
+    case 6: return launch_apply_v<TI, TE, NDOT, 32, 8, true>(ctx, op, x, y, ds, cpl);
+    default: return launch_apply_v<TI, TE, NDOT, 8, 1, false>(ctx, op, x, y, ds, cpl);
+  }
+}
+
 int apply_num_blocks(int64_t nx, int64_t ny) {
-  return (int)(((nx + kApplyThreads - 1) / kApplyThreads) * ((ny + 8 - 1) / 8));
+  const int rows = variant_rows(apply_variant());
+  return (int)(((nx + kApplyThreads - 1) / kApplyThreads) * ((ny + rows - 1) / rows));
 }
 
 int launch_apply(fdfd_ctx* ctx, const OpView<double>& op, bool te, const void* x, bool x_is_f32, c128* y, const DotSpec& ds,

@@ -1,0 +1,109 @@
+# FDFDB200.jl -- the `ccall` binding a FDFD.jl maintainer adds to route the assembly + linear-solve hot path to
+# libfdfd_b200.so (include/fdfd_b200.h).  Include it after `src/solver/modulation.jl` in `src/FDFD.jl`; with
+# ENV["FDFD_SOLVER"] == "b200" (same convention as solver.jl:10) the three L3 entry points below replace the stock
+# methods, signatures unchanged.  NOTE: Julia is not installed in the build image of this repository, so this file
+# has never been executed there; the identical C symbols are exercised from Python (tests/, ctypes).
+module FDFDB200
+
+using ..FDFD: Grid, Device, ModulatedDevice, AbstractDevice, Polarization, TM, TE, FieldTM, FieldTE,
+              setup_mode!, Float
+import ..FDFD: solve, eigenfrequency
+
+const LIB = get(ENV, "FDFD_B200_LIB", "libfdfd_b200")
+
+struct CGrid            # fdfd_grid_t  (mirrors Grid{2}, src/grid.jl:7-13)
+    Nx::Int64; Ny::Int64; Npml_x::Int64; Npml_y::Int64
+    x0::Float64; x1::Float64; y0::Float64; y1::Float64; L0::Float64
+end
+CGrid(g::Grid{2}) = CGrid(g.N[1], g.N[2], g.Npml[1], g.Npml[2], g.bounds[1][1], g.bounds[2][1],
+                          g.bounds[1][2], g.bounds[2][2], g.L₀)
+
+mutable struct COpts    # fdfd_solve_opts_t
+    solver::Int32; precond::Int32; tol::Float64; maxit::Int32; mg_precision::Int32; mg_cycle::Int32
+    mg_wdepth::Int32; mg_nu1::Int32; mg_nu2::Int32; mg_coarse_sweeps::Int32
+    mg_beta::Float64; mg_wjac::Float64; mg_wline::Float64; check_every::Int32; verbose::Int32
+    mg_shift_growth::Float64; mg_max_levels::Int32; use_graph::Int32
+    COpts() = (o = new(); ccall((:fdfd_default_opts, LIB), Cvoid, (Ref{COpts},), o); o)
+end
+
+mutable struct CInfo    # fdfd_info_t
+    iters::Int32; flag::Int32; relres::Float64; setup_ms::Float64; solve_ms::Float64; total_ms::Float64
+    launches::Int64; restarts::Int32; mg_levels::Int32
+    CInfo() = new(0, 0, 0.0, 0.0, 0.0, 0.0, 0, 0, 0)
+end
+
+const CTX = Ref{Ptr{Cvoid}}(C_NULL)
+function ctx()
+    if CTX[] == C_NULL
+        st = ccall((:fdfd_ctx_create, LIB), Cint, (Cint, Ptr{Cvoid}, Ref{Ptr{Cvoid}}),
+                   parse(Int, get(ENV, "FDFD_B200_DEVICE", "0")), C_NULL, CTX)
+        st == 0 || error("fdfd_b200: ", unsafe_string(ccall((:fdfd_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+    end
+    return CTX[]
+end
+check(st) = st == 0 || error("fdfd_b200: ", unsafe_string(ccall((:fdfd_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx())))
+enabled() = haskey(ENV, "FDFD_SOLVER") && lowercase(ENV["FDFD_SOLVER"]) == "b200"
+
+"solve(d::Device, pol) -- drop-in for src/solver/driven.jl:4-59"
+function solve_b200(d::Device{2}, pol::Polarization=TM)
+    g = CGrid(d.grid); (Nx, Ny) = size(d.grid); Nω = length(d.ω)
+    fields = pol == TM ? Array{FieldTM}(undef, Nω) : Array{FieldTE}(undef, Nω)
+    opts = COpts()
+    for i in eachindex(d.ω)
+        ω = d.ω[i]
+        length(d.modes) > 0 && (d.src = zeros(Complex, size(d.grid)))          # driven.jl:15
+        for mode in d.modes                                                   # mode source stays in Julia (<=100 unknowns)
+            setup_mode!(d, TM, ω, mode.neff, mode.pt, mode.dir, mode.width)
+        end
+        ϵ = ComplexF64.(d.ϵᵣ); src = ComplexF64.(d.src)                       # Array{Complex} is boxed: convert (SURVEY §9)
+        out = Array{ComplexF64}(undef, Nx, Ny, 3); info = CInfo()
+        GC.@preserve ϵ src out check(ccall((:fdfd_solve_driven, LIB), Cint,
+            (Ptr{Cvoid}, Ref{CGrid}, Cint, Cint, Ref{Float64}, Ptr{ComplexF64}, Ptr{ComplexF64}, Cint, Ref{COpts},
+             Ptr{ComplexF64}, Ref{CInfo}),
+            ctx(), g, Int32(pol), 1, ω, ϵ, src, 0, opts, out, info))
+        @info "fdfd_b200: $(info.iters) iterations, relres $(info.relres), $(info.solve_ms) ms"
+        fields[i] = pol == TM ? FieldTM(d.grid, ω, out) : FieldTE(d.grid, ω, out)  # data.jl:56,71
+    end
+    Nω == 1 && return fields[1]
+    return fields
+end
+
+"solve(d::ModulatedDevice) -- drop-in for src/solver/modulation.jl:35-119"
+function solve_b200(d::ModulatedDevice{2})
+    g = CGrid(d.grid); (Nx, Ny) = size(d.grid); Nω = length(d.ω); nf = 2 * d.nsidebands + 1
+    fields = Array{FieldTM}(undef, Nω, nf); opts = COpts()
+    for i in eachindex(d.ω)
+        ω = d.ω[i]; ωn = ω .+ d.Ω * (-d.nsidebands:1:d.nsidebands)
+        length(d.modes) > 0 && (d.src = zeros(Complex, size(d.grid)))
+        for mode in d.modes
+            setup_mode!(d, TM, ω, mode.neff, mode.pt, mode.dir, mode.width)
+        end
+        ϵ = ComplexF64.(d.ϵᵣ); Δϵ = ComplexF64.(d.Δϵᵣ); src = ComplexF64.(d.src)
+        out = Array{ComplexF64}(undef, Nx, Ny, 3, nf); info = CInfo()
+        GC.@preserve ϵ Δϵ src out check(ccall((:fdfd_solve_modulated, LIB), Cint,
+            (Ptr{Cvoid}, Ref{CGrid}, Float64, Float64, Cint, Cint, Ptr{ComplexF64}, Ptr{ComplexF64}, Ptr{ComplexF64},
+             Ref{COpts}, Ptr{ComplexF64}, Ref{CInfo}),
+            ctx(), g, ω, d.Ω, d.nsidebands, d.sharedpml, ϵ, Δϵ, src, opts, out, info))
+        for j = 1:nf
+            fields[i, j] = FieldTM(d.grid, ωn[j], out[:, :, :, j])
+        end
+    end
+    return fields
+end
+
+const WHICH = Dict(:LM => 0, :LR => 1, :SR => 2, :LI => 3, :SI => 4)
+
+"eigenfrequency(d, pol, nev; which) -- drop-in for src/solver/eigen.jl:69-115"
+function eigenfrequency_b200(d::AbstractDevice{2}, pol::Polarization, nev::Int; which::Symbol=:LM)
+    g = CGrid(d.grid); (Nx, Ny) = size(d.grid)
+    ϵ = ComplexF64.(d.ϵᵣ); ω = Array{ComplexF64}(undef, nev); out = Array{ComplexF64}(undef, Nx, Ny, 3, nev)
+    opts = COpts(); info = CInfo()
+    GC.@preserve ϵ ω out check(ccall((:fdfd_eigenfrequency, LIB), Cint,
+        (Ptr{Cvoid}, Ref{CGrid}, Cint, Float64, Cint, Cint, Cint, Ptr{ComplexF64}, Ref{COpts}, Ptr{ComplexF64},
+         Ptr{ComplexF64}, Ref{CInfo}),
+        ctx(), g, Int32(pol), d.ω[1], nev, WHICH[which], 0, ϵ, opts, ω, out, info))
+    F = pol == TM ? FieldTM : FieldTE
+    return (ω, [F(d.grid, ω[i], out[:, :, :, i]) for i = 1:nev])
+end
+
+end # module
