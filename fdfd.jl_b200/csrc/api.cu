@@ -39,6 +39,8 @@ MGParams mg_params_from(const fdfd_solve_opts_t& o) {
   m.coarse_sweeps = std::max(1, o.mg_coarse_sweeps);
   m.beta = o.mg_beta; m.wjac = o.mg_wjac; m.wline = o.mg_wline;
   m.shift_growth = o.mg_shift_growth; if (o.mg_max_levels > 0) m.max_levels = o.mg_max_levels;
+  if (const char* e = getenv("FDFD_MG_PAD")) m.pad = atoi(e);    // diagnostics only
+  if (const char* e = getenv("FDFD_MG_MINN")) m.min_n = atoi(e);
   return m;
 }
 

@@ -70,7 +70,7 @@ extern "C" void fdfd_default_opts(fdfd_solve_opts_t* o) {
   o->maxit = 20000;
   o->mg_precision = FDFD_MG_F32;
   o->mg_cycle = FDFD_CYCLE_W;
-  o->mg_wdepth = 4;
+  o->mg_wdepth = 2;
   o->mg_nu1 = 1; o->mg_nu2 = 1;
   o->mg_coarse_sweeps = 4;
   o->mg_beta = 0.5;
@@ -194,9 +194,19 @@ void host_coef_level(const fdfd_grid_t& g, double omega, int ordering, double sc
                      int64_t nxl, int64_t nyl, Coef1D& c) {
   auto one = [&](int dir, int64_t nl, double dw, std::vector<std::complex<double>>& cm, std::vector<std::complex<double>>& cp) {
     std::vector<std::complex<double>> sf(nl), sb(nl);
+    // coarse s-factors = averages of the continuous profile over the coarse edge (backward) / dual cell (forward), so
+    // every level keeps the PML's total complex stretched length  X = int S dp  (point sampling of the steep
+    // (l/Tw)^3.5 profile does not, and the cycle diverges when the PML is thinner than a coarse cell).  With
+    // stride 1 this is exactly the reference: sb_i = S(i), sf_i = S(i + 0.5)  (pml.jl:14-27).
     for (int64_t I = 0; I < nl; ++I) {
-      sb[I] = 1.0 / host_sprofile(g, dir, omega, 1.0 + (double)(I * stride));
-      sf[I] = 1.0 / host_sprofile(g, dir, omega, 1.0 + (double)(I * stride) + 0.5 * (double)stride);
+      const double pi = 1.0 + (double)(I * stride);
+      std::complex<double> ab(0, 0), af(0, 0);
+      for (int64_t j = 0; j < stride; ++j) {
+        ab += host_sprofile(g, dir, omega, pi - 0.5 * (double)stride + (double)j + 0.5);
+        af += host_sprofile(g, dir, omega, pi + (double)j + 0.5);
+      }
+      sb[I] = (double)stride / ab;
+      sf[I] = (double)stride / af;
     }
     coef_from_inv(sf, sb, 1.0 / (dw * (double)stride), scale, ordering, cm, cp);
   };

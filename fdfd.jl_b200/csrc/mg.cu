@@ -69,32 +69,30 @@ __global__ void k_level_setup(int64_t nx, int64_t ny, const c128* __restrict__ e
   }
 }
 
-// 1-D transfer weights of coarse point I (fine 2I): centre 1/2, left/right 1/4 when that odd fine point exists
-__device__ __forceinline__ void fw_weights(int64_t I, int64_t nf, int64_t nc, int64_t idx[3], double w[3]) {
-  const bool even = (nf % 2) == 0;
-  idx[1] = 2 * I; w[1] = 0.5;
-  if (I == 0) { idx[0] = nf - 1; w[0] = even ? 0.25 : 0.0; } else { idx[0] = 2 * I - 1; w[0] = 0.25; }
-  if (2 * I + 1 <= nf - 1) { idx[2] = 2 * I + 1; w[2] = 0.25; } else { idx[2] = 0; w[2] = 0.0; }
-  (void)nc;
+// 1-D transfer stencil of coarse point I (fine 2I): fine indices of its left / centre / right contributors.  The
+// weights come from per-level arrays built on the host (Galerkin-consistent in the stretched coordinate, see setup).
+__device__ __forceinline__ void tr_index(int64_t I, int64_t nf, int64_t idx[3]) {
+  idx[1] = 2 * I;
+  idx[0] = I == 0 ? nf - 1 : 2 * I - 1;           // weight is 0 when that point is itself a coarse point (odd nf seam)
+  idx[2] = 2 * I + 1 <= nf - 1 ? 2 * I + 1 : 0;   // weight is 0 when missing
 }
 
-// eps restriction: normalised full weighting (an average)
-__global__ void k_restrict_eps(int64_t nxf, int64_t nyf, int64_t nxc, int64_t nyc, const c128* __restrict__ ef,
-                               c128* __restrict__ ec) {
+// eps restriction with the same (volume weighted) restriction as the residual
+__global__ void k_restrict_eps(int64_t nxf, int64_t nyf, int64_t nxc, int64_t nyc, const c128* __restrict__ rx,
+                               const c128* __restrict__ ry, const c128* __restrict__ ef, c128* __restrict__ ec) {
   const int64_t Nc = nxc * nyc;
   for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < Nc; n += (int64_t)gridDim.x * blockDim.x) {
     const int64_t I = n % nxc, J = n / nxc;
-    int64_t xi[3], yi[3]; double wx[3], wy[3];
-    fw_weights(I, nxf, nxc, xi, wx); fw_weights(J, nyf, nyc, yi, wy);
-    double sr = 0, si = 0, sw = 0;
+    int64_t xi[3], yi[3];
+    tr_index(I, nxf, xi); tr_index(J, nyf, yi);
+    c128 acc(0.0, 0.0);
     for (int b = 0; b < 3; ++b)
       for (int a = 0; a < 3; ++a) {
-        const double w = wx[a] * wy[b];
-        if (w == 0.0) continue;
-        const c128 e = ef[xi[a] + nxf * yi[b]];
-        sr += w * e.x; si += w * e.y; sw += w;
+        const c128 w = rx[3 * I + a] * ry[3 * J + b];
+        if (w.x == 0.0 && w.y == 0.0) continue;
+        acc += w * ef[xi[a] + nxf * yi[b]];
       }
-    ec[n] = c128(sr / sw, si / sw);
+    ec[n] = acc;
   }
 }
 
@@ -221,32 +219,39 @@ __global__ void k_lines(int64_t n, int K, const cplx<T>* __restrict__ mult, cons
   }
 }
 
-// ---- residual + full-weighting restriction (coarse-point-centric) --------------------------------------
+// ---- residual + restriction (coarse-point-centric).  r_c(I,J) = sum RX[I][a] RY[J][b] r(xi[a], yi[b]) with
+// RX = P^T V / (2 V_c): transpose of the operator-dependent interpolation, weighted by the stretched cell volumes
 template <typename T, bool TE>
 __global__ void k_resid_restrict(OpView<T> op, const cplx<T>* __restrict__ u, const cplx<T>* __restrict__ f,
-                                 int64_t nxc, int64_t nyc, cplx<T>* __restrict__ fc, const int* __restrict__ done) {
+                                 int64_t nxc, int64_t nyc, const cplx<T>* __restrict__ rx, const cplx<T>* __restrict__ ry,
+                                 cplx<T>* __restrict__ fc, const int* __restrict__ done) {
   if (done && *done) return;
   const int64_t I = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t J = blockIdx.y;
   if (I >= nxc) return;
-  int64_t xi[3], yi[3]; double wx[3], wy[3];
-  fw_weights(I, op.nx, nxc, xi, wx); fw_weights(J, op.ny, nyc, yi, wy);
+  int64_t xi[3], yi[3];
+  tr_index(I, op.nx, xi); tr_index(J, op.ny, yi);
   cplx<T> acc(T(0), T(0));
 #pragma unroll
-  for (int b = 0; b < 3; ++b)
+  for (int b = 0; b < 3; ++b) {
+    const cplx<T> wy = ry[3 * J + b];
+    if (wy.x == T(0) && wy.y == T(0)) continue;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      const T w = T(wx[a] * wy[b]);
-      if (w == T(0)) continue;
-      acc += w * residual_at<T, TE>(op, u, f, xi[a], yi[b], nullptr);
+      const cplx<T> wx = rx[3 * I + a];
+      if (wx.x == T(0) && wx.y == T(0)) continue;
+      acc += (wx * wy) * residual_at<T, TE>(op, u, f, xi[a], yi[b], nullptr);
     }
+  }
   fc[I + nxc * J] = acc;
 }
 
-// ---- bilinear prolongation + correction ------------------------------------------------------------------
+// ---- operator-dependent prolongation + correction: odd fine points interpolate with the complex weights
+// wl/wr = conductance-weighted (linear in the STRETCHED coordinate), even points inject
 template <typename T>
-__global__ void k_prolong_add(int64_t nx, int64_t ny, int64_t nxc, int64_t nyc, const cplx<T>* __restrict__ uc,
-                              cplx<T>* __restrict__ u, const int* __restrict__ done) {
+__global__ void k_prolong_add(int64_t nx, int64_t ny, int64_t nxc, int64_t nyc, const cplx<T>* __restrict__ pwx,
+                              const cplx<T>* __restrict__ pwy, const cplx<T>* __restrict__ uc, cplx<T>* __restrict__ u,
+                              const int* __restrict__ done) {
   if (done && *done) return;
   const int64_t ix = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t iy = blockIdx.y;
@@ -255,18 +260,67 @@ __global__ void k_prolong_add(int64_t nx, int64_t ny, int64_t nxc, int64_t nyc, 
   const bool ox = ix & 1, oy = iy & 1;
   const int64_t I1 = ox ? (I0 + 1 == nxc ? 0 : I0 + 1) : I0;
   const int64_t J1 = oy ? (J0 + 1 == nyc ? 0 : J0 + 1) : J0;
-  cplx<T> v = uc[I0 + nxc * J0];
-  if (ox) v += uc[I1 + nxc * J0];
+  const cplx<T> one(T(1), T(0)), zero(T(0), T(0));
+  const cplx<T> wxl = ox ? pwx[ix] : one, wxr = ox ? pwx[nx + ix] : zero;
+  const cplx<T> wyl = oy ? pwy[iy] : one, wyr = oy ? pwy[ny + iy] : zero;
+  cplx<T> lo = wxl * uc[I0 + nxc * J0];
+  if (ox) lo += wxr * uc[I1 + nxc * J0];
+  cplx<T> v = wyl * lo;
   if (oy) {
-    cplx<T> w = uc[I0 + nxc * J1];
-    if (ox) w += uc[I1 + nxc * J1];
-    v += w;
+    cplx<T> hi = wxl * uc[I0 + nxc * J1];
+    if (ox) hi += wxr * uc[I1 + nxc * J1];
+    v += wyr * hi;
   }
-  const T sc = (ox ? T(0.5) : T(1)) * (oy ? T(0.5) : T(1));
-  u[ix + nx * iy] += sc * v;
+  u[ix + nx * iy] += v;
 }
 
 }  // namespace
+
+// ---- host: Galerkin-consistent 1-D hierarchy in the stretched coordinate -------------------------------------
+// E[i] = stretched length (in cell units) of the edge between points i-1 and i, V[i] = stretched volume of point i.
+//   f.b ordering (driven.jl:35):      E = s_backward,            V = s_forward
+//   b.f ordering (modulation.jl:82):  E[i] = s_forward[i-1],     V = s_backward
+// row i of the 1-D operator:  (scale/h^2) / V[i] * ( (u[i-1]-u[i])/E[i] + (u[i+1]-u[i])/E[i+1] ).
+// Coarsening i = 2I: interpolation weights from the edge conductances (linear in the stretched coordinate),
+// coarse edge = sum of its fine edges, coarse volume = P^T V, restriction = P^T V / (2 V_c).  Odd sizes leave one
+// short coarse edge between the last and the first point (exact, no approximation).
+using cdh = std::complex<double>;
+struct Hier1D {
+  std::vector<std::vector<cdh>> E, V, wl, wr, R;  // per level; R[l] restricts level l -> l+1 (3 per coarse point)
+};
+static void build_hier1d(const std::vector<cdh>& E0, const std::vector<cdh>& V0, int nlev, Hier1D& H) {
+  H.E.assign(1, E0); H.V.assign(1, V0); H.wl.clear(); H.wr.clear(); H.R.clear();
+  for (int l = 0; l < nlev; ++l) {
+    const std::vector<cdh>& E = H.E[l]; const std::vector<cdh>& V = H.V[l];
+    const int64_t n = (int64_t)E.size();
+    std::vector<cdh> wl(n), wr(n);
+    for (int64_t i = 0; i < n; ++i) {
+      const cdh a = 1.0 / E[i], ap = 1.0 / E[(i + 1) % n];
+      wl[i] = a / (a + ap); wr[i] = ap / (a + ap);
+    }
+    H.wl.push_back(wl); H.wr.push_back(wr);
+    if (l == nlev - 1) break;
+    const int64_t nc = (n + 1) / 2;
+    std::vector<cdh> Ec(nc), Vc(nc), R(3 * nc);
+    for (int64_t I = 0; I < nc; ++I) {
+      const int64_t i = 2 * I;
+      const bool has_l = !(I == 0 && (n % 2) == 1) && n > 1;
+      const bool has_r = i + 1 <= n - 1;
+      const int64_t il = (i - 1 + n) % n, ir = has_r ? i + 1 : 0;
+      const cdh nl = has_l ? wr[il] * V[il] : cdh(0, 0), nc0 = V[i], nr = has_r ? wl[ir] * V[ir] : cdh(0, 0);
+      Vc[I] = (nl + nc0 + nr) / 2.0;
+      R[3 * I + 0] = nl / (2.0 * Vc[I]); R[3 * I + 1] = nc0 / (2.0 * Vc[I]); R[3 * I + 2] = nr / (2.0 * Vc[I]);
+      Ec[I] = (E[i] + (has_l ? E[il] : cdh(0, 0))) / 2.0;
+    }
+    H.R.push_back(R); H.E.push_back(Ec); H.V.push_back(Vc);
+  }
+}
+static void hier_coefs(const Hier1D& H, int l, double scale_over_h2, std::vector<cdh>& cm, std::vector<cdh>& cp) {
+  const std::vector<cdh>& E = H.E[l]; const std::vector<cdh>& V = H.V[l];
+  const int64_t n = (int64_t)E.size();
+  cm.resize(n); cp.resize(n);
+  for (int64_t i = 0; i < n; ++i) { cm[i] = scale_over_h2 / (V[i] * E[i]); cp[i] = scale_over_h2 / (V[i] * E[(i + 1) % n]); }
+}
 
 // ==============================================================================================
 template <typename T> int Multigrid<T>::setup(fdfd_ctx* ctx_, const FineOp& op, const MGParams& prm_) {
@@ -287,6 +341,24 @@ template <typename T> int Multigrid<T>::setup(fdfd_ctx* ctx_, const FineOp& op, 
     nx = cx; ny = cy; sizes.push_back({nx, ny});
   }
   lv.resize(sizes.size());
+  // 1-D hierarchies from the reference s-factors (not inverted) at the PML frequency
+  Hier1D HX, HY;
+  {
+    std::vector<cdh> sxf, sxb, syf, syb;
+    host_sfactor(g, 0, 1, op.omega_pml, sxf); host_sfactor(g, 0, 0, op.omega_pml, sxb);
+    host_sfactor(g, 1, 1, op.omega_pml, syf); host_sfactor(g, 1, 0, op.omega_pml, syb);
+    auto EV = [&](const std::vector<cdh>& sf, const std::vector<cdh>& sb, std::vector<cdh>& E, std::vector<cdh>& V) {
+      const int64_t n = (int64_t)sf.size();
+      E.resize(n); V.resize(n);
+      for (int64_t i = 0; i < n; ++i) {
+        if (op.ordering == FDFD_ORDER_FB) { E[i] = sb[i]; V[i] = sf[i]; }
+        else { E[i] = sf[(i + n - 1) % n]; V[i] = sb[i]; }
+      }
+    };
+    std::vector<cdh> Ex, Vx, Ey, Vy;
+    EV(sxf, sxb, Ex, Vx); EV(syf, syb, Ey, Vy);
+    build_hier1d(Ex, Vx, (int)lv.size(), HX); build_hier1d(Ey, Vy, (int)lv.size(), HY);
+  }
   size_t scratch_need = 0, line_scratch_need = 0;
   for (size_t l = 0; l < lv.size(); ++l) {
     MGLevel<T>& L = lv[l];
@@ -294,7 +366,27 @@ template <typename T> int Multigrid<T>::setup(fdfd_ctx* ctx_, const FineOp& op, 
     const int64_t N = L.nx * L.ny;
     // 1-D coefficients
     Coef1D hc;
-    if (l == 0) hc = op.hc; else host_coef_level(g, op.omega_pml, op.ordering, scale, L.stride, L.nx, L.ny, hc);
+    if (l == 0) hc = op.hc;
+    else {
+      const double hx = grid_dx(g) * (double)L.stride, hy = grid_dy(g) * (double)L.stride;
+      hier_coefs(HX, (int)l, scale / (hx * hx), hc.cxm, hc.cxp);
+      hier_coefs(HY, (int)l, scale / (hy * hy), hc.cym, hc.cyp);
+    }
+    {  // transfer weights: prolongation from level l+1 (fine-indexed wl|wr) and restriction to level l+1
+      std::vector<cplx<T>> pw; pw.reserve(2 * L.nx + 2 * L.ny);
+      for (auto* v : {&HX.wl[l], &HX.wr[l], &HY.wl[l], &HY.wr[l]}) for (auto& z : *v) pw.push_back(cplx<T>(T(z.real()), T(z.imag())));
+      CUDA_TRY(ctx, L.pw.alloc(pw.size()));
+      CUDA_TRY(ctx, cudaMemcpyAsync(L.pw.p, pw.data(), pw.size() * sizeof(cplx<T>), cudaMemcpyHostToDevice, ctx->stream));
+      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      if (l + 1 < lv.size()) {
+        std::vector<cplx<T>> rw; std::vector<c128> rwd;
+        for (auto* v : {&HX.R[l], &HY.R[l]}) for (auto& z : *v) { rw.push_back(cplx<T>(T(z.real()), T(z.imag()))); rwd.push_back(c128(z.real(), z.imag())); }
+        CUDA_TRY(ctx, L.rw.alloc(rw.size())); CUDA_TRY(ctx, L.rwd.alloc(rwd.size()));
+        CUDA_TRY(ctx, cudaMemcpyAsync(L.rw.p, rw.data(), rw.size() * sizeof(cplx<T>), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(L.rwd.p, rwd.data(), rwd.size() * sizeof(c128), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      }
+    }
     std::vector<cplx<T>> pack; pack.reserve(2 * L.nx + 2 * L.ny);
     for (auto* v : {&hc.cxm, &hc.cxp, &hc.cym, &hc.cyp}) for (auto& z : *v) pack.push_back(cplx<T>(T(z.real() * rhs_scale), T(z.imag() * rhs_scale)));
     CUDA_TRY(ctx, L.c1d.alloc(pack.size()));
@@ -308,7 +400,8 @@ template <typename T> int Multigrid<T>::setup(fdfd_ctx* ctx_, const FineOp& op, 
       CUDA_TRY(ctx, L.eps.alloc(N));
       const c128* eps_f = l == 1 ? op.eps.p : lv[l - 1].eps.p;
       const int blocks = (int)std::min<int64_t>((N + threads - 1) / threads, (int64_t)ctx->num_sms * 16);
-      k_restrict_eps<<<blocks, threads, 0, ctx->stream>>>(lv[l - 1].nx, lv[l - 1].ny, L.nx, L.ny, eps_f, L.eps.p);
+      k_restrict_eps<<<blocks, threads, 0, ctx->stream>>>(lv[l - 1].nx, lv[l - 1].ny, L.nx, L.ny, lv[l - 1].rwd.p,
+                                                        lv[l - 1].rwd.p + 3 * L.nx, eps_f, L.eps.p);
       KLAUNCH(ctx);
       eps_l = L.eps.p;
     }
@@ -423,8 +516,8 @@ template <typename T> int Multigrid<T>::cycle(int l, bool zero, int kind) {
   MGLevel<T>& C = lv[l + 1];
   {
     dim3 grid((unsigned)((C.nx + 127) / 128), (unsigned)C.ny);
-    if (te) k_resid_restrict<T, true><<<grid, 128, 0, ctx->stream>>>(L.view(), L.u.p, L.f.p, C.nx, C.ny, C.f.p, done);
-    else k_resid_restrict<T, false><<<grid, 128, 0, ctx->stream>>>(L.view(), L.u.p, L.f.p, C.nx, C.ny, C.f.p, done);
+    if (te) k_resid_restrict<T, true><<<grid, 128, 0, ctx->stream>>>(L.view(), L.u.p, L.f.p, C.nx, C.ny, L.rw.p, L.rw.p + 3 * C.nx, C.f.p, done);
+    else k_resid_restrict<T, false><<<grid, 128, 0, ctx->stream>>>(L.view(), L.u.p, L.f.p, C.nx, C.ny, L.rw.p, L.rw.p + 3 * C.nx, C.f.p, done);
     KLAUNCH(ctx);
   }
   if (kind == 2 && l < prm.wdepth) {
@@ -438,7 +531,7 @@ template <typename T> int Multigrid<T>::cycle(int l, bool zero, int kind) {
   }
   {
     dim3 grid((unsigned)((L.nx + 127) / 128), (unsigned)L.ny);
-    k_prolong_add<T><<<grid, 128, 0, ctx->stream>>>(L.nx, L.ny, C.nx, C.ny, C.u.p, L.u.p, done);
+    k_prolong_add<T><<<grid, 128, 0, ctx->stream>>>(L.nx, L.ny, C.nx, C.ny, L.pw.p, L.pw.p + 2 * L.nx, C.u.p, L.u.p, done);
     KLAUNCH(ctx);
   }
   for (int s = 0; s < prm.nu2; ++s) FDFD_TRY(smooth(l, false));

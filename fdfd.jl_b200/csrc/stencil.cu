@@ -179,10 +179,10 @@ int FineOp::build(fdfd_ctx* ctx, const fdfd_grid_t& g_, int pol_, int ordering_,
 // tuning variants (FDFD_APPLY_VARIANT): rows marched per thread, min CTAs/SM (register cap), streaming hints
 static int apply_variant() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("FDFD_APPLY_VARIANT"); v = e ? atoi(e) : 0; if (v < 0 || v > 6) v = 0; }
+  if (v < 0) { const char* e = getenv("FDFD_APPLY_VARIANT"); v = e ? atoi(e) : 0; if (v < 0 || v > 7) v = 0; }
   return v;
 }
-static int variant_rows(int v) { static const int rows[7] = {8, 8, 16, 4, 8, 16, 32}; return rows[v]; }
+static int variant_rows(int v) { static const int rows[8] = {4, 8, 16, 4, 8, 16, 32, 8}; return rows[v]; }
 
 template <typename TI, bool TE, int NDOT, int ROWS, int MINB, bool HINT>
 static int launch_apply_v(fdfd_ctx* ctx, const OpView<double>& op, const TI* x, c128* y, const DotSpec& ds, const Coupling* cpl) {
@@ -204,7 +204,8 @@ static int launch_apply_t(fdfd_ctx* ctx, const OpView<double>& op, const TI* x, 
     case 4: return launch_apply_v<TI, TE, NDOT, 8, 1, true>(ctx, op, x, y, ds, cpl);
     case 5: return launch_apply_v<TI, TE, NDOT, 16, 6, true>(ctx, op, x, y, ds, cpl);
     case 6: return launch_apply_v<TI, TE, NDOT, 32, 8, true>(ctx, op, x, y, ds, cpl);
-    default: return launch_apply_v<TI, TE, NDOT, 8, 1, false>(ctx, op, x, y, ds, cpl);
+    case 7: return launch_apply_v<TI, TE, NDOT, 8, 1, false>(ctx, op, x, y, ds, cpl);
+    default: return launch_apply_v<TI, TE, NDOT, 4, 8, true>(ctx, op, x, y, ds, cpl);
   }
 }
 

@@ -74,7 +74,7 @@ typedef struct {
   int32_t maxit;         /* Krylov iterations (default 20000) */
   int32_t mg_precision;  /* FDFD_MG_F32 | FDFD_MG_F64 (default F32) */
   int32_t mg_cycle;      /* FDFD_CYCLE_* (default W, truncated at mg_wdepth) */
-  int32_t mg_wdepth;     /* levels [0,wdepth) recurse twice in a W cycle (default 4) */
+  int32_t mg_wdepth;     /* levels [0,wdepth) recurse twice in a W cycle (default 2) */
   int32_t mg_nu1, mg_nu2;/* pre/post smoothing sweeps (default 1,1) */
   int32_t mg_coarse_sweeps; /* sweeps on the coarsest level (default 4) */
   double  mg_beta;       /* complex shift: M = L + (1 - i*beta) w^2 eps (default 0.5) */
