@@ -41,6 +41,7 @@ MGParams mg_params_from(const fdfd_solve_opts_t& o) {
   m.shift_growth = o.mg_shift_growth; if (o.mg_max_levels > 0) m.max_levels = o.mg_max_levels;
   if (const char* e = getenv("FDFD_MG_PAD")) m.pad = atoi(e);    // diagnostics only
   if (const char* e = getenv("FDFD_MG_MINN")) m.min_n = atoi(e);
+  if (const char* e = getenv("FDFD_MG_KHSTOP")) m.kh_stop = atof(e);
   return m;
 }
 

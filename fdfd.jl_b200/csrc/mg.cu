@@ -219,6 +219,118 @@ __global__ void k_lines(int64_t n, int K, const cplx<T>* __restrict__ mult, cons
   }
 }
 
+// =====================================================================================================
+// Fused smoother (2 launches per sweep instead of 4; the coarse levels are launch-latency bound):
+//   k_smooth2: residual of every point from the same iterate; Jacobi update outside the strips; residual capture
+//              for the strip columns AND the strip rows; optionally the coarse-grid correction is applied on the
+//              fly (PROLONG): the iterate it reads is u + P u_c, evaluated per stencil point, and written back.
+//   k_lines2:  all y-lines (strip columns, updating the rows outside the y-strip) and all x-lines (strip rows,
+//              including the corners) in one launch.
+// =====================================================================================================
+template <typename T> struct ProlongView {
+  int64_t nxc, nyc;
+  const cplx<T>* pwx; const cplx<T>* pwy; const cplx<T>* uc;
+};
+
+template <typename T, bool PROLONG>
+__device__ __forceinline__ cplx<T> iterate_at(const cplx<T>* __restrict__ u, const ProlongView<T>& pv, int64_t nx, int64_t ny,
+                                              int64_t ix, int64_t iy) {
+  cplx<T> v = u[ix + nx * iy];
+  if (PROLONG) {
+    const int64_t I0 = ix >> 1, J0 = iy >> 1;
+    const bool ox = ix & 1, oy = iy & 1;
+    const int64_t I1 = ox ? (I0 + 1 == pv.nxc ? 0 : I0 + 1) : I0;
+    const int64_t J1 = oy ? (J0 + 1 == pv.nyc ? 0 : J0 + 1) : J0;
+    const cplx<T> one(T(1), T(0)), zero(T(0), T(0));
+    const cplx<T> wxl = ox ? pv.pwx[ix] : one, wxr = ox ? pv.pwx[nx + ix] : zero;
+    const cplx<T> wyl = oy ? pv.pwy[iy] : one, wyr = oy ? pv.pwy[ny + iy] : zero;
+    cplx<T> lo = wxl * pv.uc[I0 + pv.nxc * J0];
+    if (ox) lo += wxr * pv.uc[I1 + pv.nxc * J0];
+    cplx<T> c = wyl * lo;
+    if (oy) {
+      cplx<T> hi = wxl * pv.uc[I0 + pv.nxc * J1];
+      if (ox) hi += wxr * pv.uc[I1 + pv.nxc * J1];
+      c += wyr * hi;
+    }
+    v += c;
+  }
+  return v;
+}
+
+template <typename T, bool TE, bool ZERO, bool PROLONG>
+__global__ void __launch_bounds__(kMgThreads)
+k_smooth2(OpView<T> op, const cplx<T>* __restrict__ u, const cplx<T>* __restrict__ f, cplx<T>* __restrict__ out,
+          cplx<T>* __restrict__ rxs, cplx<T>* __restrict__ rys, int npx, int npy, T wj, ProlongView<T> pv,
+          const int* __restrict__ done) {
+  if (done && *done) return;
+  const int64_t nx = op.nx, ny = op.ny;
+  const int64_t ix = blockIdx.x * (int64_t)kMgThreads + threadIdx.x;
+  if (ix >= nx) return;
+  const bool xs = in_strip(ix, nx, npx);
+  const int64_t ixm = ix == 0 ? nx - 1 : ix - 1, ixp = ix + 1 == nx ? 0 : ix + 1;
+#pragma unroll
+  for (int r = 0; r < kMgRows; ++r) {
+    const int64_t iy = blockIdx.y * (int64_t)kMgRows + r;
+    if (iy >= ny) break;
+    const int64_t n = ix + nx * iy;
+    const bool ys = in_strip(iy, ny, npy);
+    const int64_t iym = iy == 0 ? ny - 1 : iy - 1, iyp = iy + 1 == ny ? 0 : iy + 1;
+    cplx<T> W, E, S, Nn, C;
+    row_coefs<T, TE>(op, ix, iy, ixp, iyp, W, E, S, Nn, C);
+    cplx<T> u0(T(0), T(0)), res = f[n];
+    if (!ZERO) {
+      u0 = iterate_at<T, PROLONG>(u, pv, nx, ny, ix, iy);
+      res -= C * u0;
+      res -= W * iterate_at<T, PROLONG>(u, pv, nx, ny, ixm, iy);
+      res -= E * iterate_at<T, PROLONG>(u, pv, nx, ny, ixp, iy);
+      res -= S * iterate_at<T, PROLONG>(u, pv, nx, ny, ix, iym);
+      res -= Nn * iterate_at<T, PROLONG>(u, pv, nx, ny, ix, iyp);
+    }
+    if (xs) rxs[strip_line(ix, nx, npx) * ny + iy] = res;
+    if (ys) rys[strip_line(iy, ny, npy) * nx + ix] = res;
+    out[n] = (xs || ys) ? u0 : u0 + wj * cdiv(res, C);
+  }
+}
+
+template <typename T>
+__global__ void k_lines2(int64_t nx, int64_t ny, int npx, int npy, int Ky, int Kx, const cplx<T>* __restrict__ mult_y,
+                         const cplx<T>* __restrict__ mult_x, const cplx<T>* __restrict__ rxs, const cplx<T>* __restrict__ rys,
+                         cplx<T>* __restrict__ out, T wl, cplx<T>* __restrict__ gscratch, const int* __restrict__ done) {
+  if (done && *done) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const bool ymode = (int)blockIdx.x < 2 * npx;       // y-line of a strip column, else x-line of a strip row
+  const int64_t c = ymode ? blockIdx.x : blockIdx.x - 2 * npx;
+  const int64_t n = ymode ? ny : nx;
+  const int K = ymode ? Ky : Kx;
+  const int64_t nmax = nx > ny ? nx : ny;
+  cplx<T>* d0 = gscratch ? gscratch + (size_t)blockIdx.x * 2 * nmax : reinterpret_cast<cplx<T>*>(smem_raw);
+  cplx<T>* d1 = d0 + n;
+  const cplx<T>* mult = ymode ? mult_y : mult_x;
+  const cplx<T>* alpha = mult + (size_t)c * (2 * K + 1) * n;
+  const cplx<T>* gamma = alpha + (size_t)K * n;
+  const cplx<T>* binv = gamma + (size_t)K * n;
+  const cplx<T>* rbuf = (ymode ? rxs : rys) + c * n;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) d0[i] = rbuf[i];
+  __syncthreads();
+  for (int k = 0; k < K; ++k) {
+    const int64_t s = (int64_t)1 << k;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+      cplx<T> v = d0[i];
+      if (i >= s) v += alpha[(size_t)k * n + i] * d0[i - s];
+      if (i + s < n) v += gamma[(size_t)k * n + i] * d0[i + s];
+      d1[i] = v;
+    }
+    __syncthreads();
+    cplx<T>* t = d0; d0 = d1; d1 = t;
+  }
+  const int64_t fixed = strip_index(c, ymode ? nx : ny, ymode ? npx : npy);
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    if (ymode && in_strip(i, ny, npy)) continue;  // corners belong to the x-lines
+    const int64_t idx = ymode ? fixed + nx * i : i + nx * fixed;
+    out[idx] += wl * (d0[i] * binv[i]);
+  }
+}
+
 // ---- residual + restriction (coarse-point-centric).  r_c(I,J) = sum RX[I][a] RY[J][b] r(xi[a], yi[b]) with
 // RX = P^T V / (2 V_c): transpose of the operator-dependent interpolation, weighted by the stretched cell volumes
 template <typename T, bool TE>
@@ -335,7 +447,12 @@ template <typename T> int Multigrid<T>::setup(fdfd_ctx* ctx_, const FineOp& op, 
   std::vector<std::pair<int64_t, int64_t>> sizes;
   int64_t nx = g.Nx, ny = g.Ny;
   sizes.push_back({nx, ny});
+  // stop coarsening once the coarsest level is mass dominated even in vacuum (k0 h >= kh_stop): there damped Jacobi
+  // alone converges (|kappa| >> 4) and deeper levels would only add latency-bound launches
+  const double k0 = op.omega * std::sqrt(eps0 * mu0);
   while ((int)sizes.size() < prm.max_levels) {
+    const double hl = std::min(grid_dx(g), grid_dy(g)) * (double)((int64_t)1 << (sizes.size() - 1));
+    if (prm.kh_stop > 0 && k0 * hl >= prm.kh_stop) break;
     const int64_t cx = (nx + 1) / 2, cy = (ny + 1) / 2;
     if (cx < prm.min_n || cy < prm.min_n || cx < 2 || cy < 2) break;
     nx = cx; ny = cy; sizes.push_back({nx, ny});
@@ -446,6 +563,7 @@ template <typename T> int Multigrid<T>::setup(fdfd_ctx* ctx_, const FineOp& op, 
     }
   }
   CUDA_TRY(ctx, spare.alloc((size_t)g.Nx * g.Ny));
+  for (auto& L : lv) { const int64_t nmax = std::max(L.nx, L.ny); if ((size_t)2 * nmax * sizeof(cplx<T>) > 200 * 1024) line_scratch_need = std::max(line_scratch_need, (size_t)(2 * L.npx + 2 * L.npy) * 2 * nmax); }
   CUDA_TRY(ctx, pcr_scratch.alloc(scratch_need));
   if (line_scratch_need) CUDA_TRY(ctx, line_scratch.alloc(line_scratch_need));
   for (size_t l = 0; l < lv.size(); ++l) {
@@ -464,12 +582,13 @@ template <typename T> int Multigrid<T>::setup(fdfd_ctx* ctx_, const FineOp& op, 
   }
   // opt in to large dynamic shared memory for the line kernel
   CUDA_TRY(ctx, cudaFuncSetAttribute(k_lines<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CUDA_TRY(ctx, cudaFuncSetAttribute(k_lines2<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   pcr_scratch.release();
   return FDFD_OK;
 }
 
-template <typename T> int Multigrid<T>::smooth(int l, bool zero) {
+template <typename T> int Multigrid<T>::smooth_classic(int l, bool zero) {
   MGLevel<T>& L = lv[l];
   const OpView<T> op = L.view();
   dim3 grid((unsigned)((L.nx + kMgThreads - 1) / kMgThreads), (unsigned)((L.ny + kMgRows - 1) / kMgRows));
@@ -505,6 +624,44 @@ template <typename T> int Multigrid<T>::smooth(int l, bool zero) {
   return FDFD_OK;
 }
 
+template <typename T> int Multigrid<T>::smooth(int l, bool zero, bool prolong) {
+  static const bool classic = []() { const char* e = getenv("FDFD_MG_SMOOTHER"); return e && atoi(e) == 4; }();
+  MGLevel<T>& L = lv[l];
+  if (classic) {
+    if (prolong) {
+      MGLevel<T>& C = lv[l + 1];
+      dim3 grid((unsigned)((L.nx + 127) / 128), (unsigned)L.ny);
+      k_prolong_add<T><<<grid, 128, 0, ctx->stream>>>(L.nx, L.ny, C.nx, C.ny, L.pw.p, L.pw.p + 2 * L.nx, C.u.p, L.u.p, done);
+      KLAUNCH(ctx);
+    }
+    return smooth_classic(l, zero);
+  }
+  const OpView<T> op = L.view();
+  dim3 grid((unsigned)((L.nx + kMgThreads - 1) / kMgThreads), (unsigned)((L.ny + kMgRows - 1) / kMgRows));
+  const T wj = T(prm.wjac), wl = T(prm.wline);
+  cplx<T>* out = zero ? L.u.p : L.tmp.p;
+  ProlongView<T> pv{0, 0, nullptr, nullptr, nullptr};
+  if (prolong) { MGLevel<T>& C = lv[l + 1]; pv = ProlongView<T>{C.nx, C.ny, L.pw.p, L.pw.p + 2 * L.nx, C.u.p}; }
+#define SM2(TEV, ZV, PV) k_smooth2<T, TEV, ZV, PV><<<grid, kMgThreads, 0, ctx->stream>>>(op, L.u.p, L.f.p, out, L.rxs.p, L.rys.p, L.npx, L.npy, wj, pv, done)
+  if (te) { if (zero) SM2(true, true, false); else if (prolong) SM2(true, false, true); else SM2(true, false, false); }
+  else    { if (zero) SM2(false, true, false); else if (prolong) SM2(false, false, true); else SM2(false, false, false); }
+#undef SM2
+  KLAUNCH(ctx);
+  if (!zero) std::swap(L.u.p, L.tmp.p);
+  const int nlines = 2 * L.npx + 2 * L.npy;
+  if (nlines > 0) {
+    const int64_t nmax = std::max(L.nx, L.ny);
+    const size_t smem = (size_t)2 * nmax * sizeof(cplx<T>);
+    const bool use_g = smem > 200 * 1024;
+    const int threads = (int)std::min<int64_t>(1024, std::max<int64_t>(32, ((nmax + 31) / 32) * 32));
+    k_lines2<T><<<nlines, threads, use_g ? 0 : smem, ctx->stream>>>(L.nx, L.ny, L.npx, L.npy, L.Ky, L.Kx, L.pcr_y.p, L.pcr_x.p,
+                                                                   L.rxs.p, L.rys.p, L.u.p, wl, use_g ? line_scratch.p : nullptr, done);
+    KLAUNCH(ctx);
+  }
+  CUDA_TRY(ctx, cudaGetLastError());
+  return FDFD_OK;
+}
+
 // kind: 0 = V, 1 = F, 2 = W (W recursion only while l < wdepth)
 template <typename T> int Multigrid<T>::cycle(int l, bool zero, int kind) {
   MGLevel<T>& L = lv[l];
@@ -529,12 +686,12 @@ template <typename T> int Multigrid<T>::cycle(int l, bool zero, int kind) {
   } else {
     FDFD_TRY(cycle(l + 1, true, kind == 2 ? 0 : kind));
   }
-  {
+  if (prm.nu2 < 1) {
     dim3 grid((unsigned)((L.nx + 127) / 128), (unsigned)L.ny);
     k_prolong_add<T><<<grid, 128, 0, ctx->stream>>>(L.nx, L.ny, C.nx, C.ny, L.pw.p, L.pw.p + 2 * L.nx, C.u.p, L.u.p, done);
     KLAUNCH(ctx);
   }
-  for (int s = 0; s < prm.nu2; ++s) FDFD_TRY(smooth(l, false));
+  for (int s = 0; s < prm.nu2; ++s) FDFD_TRY(smooth(l, false, s == 0));  // the first post-sweep applies the correction
   CUDA_TRY(ctx, cudaGetLastError());
   return FDFD_OK;
 }

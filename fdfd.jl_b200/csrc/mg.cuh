@@ -45,6 +45,7 @@ struct MGParams {
   int cycle = FDFD_CYCLE_W, wdepth = 4, nu1 = 1, nu2 = 1, coarse_sweeps = 4;
   double beta = 0.5, wjac = 0.8, wline = 0.7, shift_growth = 0.0;
   int min_n = 2, pad = 1, max_levels = 32;
+  double kh_stop = 4.0;
 };
 
 template <typename T> struct Multigrid {
@@ -67,5 +68,6 @@ template <typename T> struct Multigrid {
 
  private:
   int cycle(int l, bool zero, int kind);
-  int smooth(int l, bool zero);
+  int smooth(int l, bool zero, bool prolong = false);
+  int smooth_classic(int l, bool zero);
 };
