@@ -462,6 +462,13 @@ class Problem:
         check(lib().fdfd_problem_bench_apply(self._h, nrep, C.byref(ms)), self.ctx.handle)
         return ms.value
 
+    def history(self, nmax=100000):
+        """relative (recurrence) residual per iteration of the last solve"""
+        out = np.empty(nmax, dtype=np.float64)
+        n = C.c_int32()
+        check(lib().fdfd_problem_get_history(self._h, ptr(out), nmax, C.byref(n)), self.ctx.handle)
+        return out[:n.value].copy()
+
     def precond(self, v):
         vin = as_c128(v, self.grid.N)
         out = np.empty(self.grid.N, dtype=np.complex128, order="F")

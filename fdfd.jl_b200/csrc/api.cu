@@ -174,6 +174,20 @@ extern "C" int fdfd_problem_bench_apply(fdfd_problem* P, int nrep, double* ms_pe
   return FDFD_OK;
 }
 
+extern "C" int fdfd_problem_get_history(fdfd_problem* P, double* out, int n, int* written) {
+  if (!P) return FDFD_ERR_ARG;
+  fdfd_ctx* ctx = P->ctx;
+  ARG_CHECK(ctx, out && n > 0 && written, "bad arguments");
+  const KScal h = *P->w.h_scal;
+  const int cnt = std::min(std::min(n, h.iter + 1), (int)P->w.hist.n);
+  std::vector<double> tmp(cnt);
+  CUDA_TRY(ctx, cudaMemcpyAsync(tmp.data(), P->w.hist.p, cnt * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < cnt; ++k) out[k] = k == 0 ? 1.0 : std::sqrt(tmp[k] / h.bnorm2);
+  *written = cnt;
+  return FDFD_OK;
+}
+
 extern "C" int fdfd_problem_precond(fdfd_problem* P, const fdfd_c128* in, fdfd_c128* out) {
   if (!P) return FDFD_ERR_ARG;
   fdfd_ctx* ctx = P->ctx;

@@ -72,7 +72,7 @@ extern "C" void fdfd_default_opts(fdfd_solve_opts_t* o) {
   o->mg_cycle = FDFD_CYCLE_W;
   o->mg_wdepth = 2;
   o->mg_nu1 = 1; o->mg_nu2 = 1;
-  o->mg_coarse_sweeps = 4;
+  o->mg_coarse_sweeps = 2;
   o->mg_beta = 0.5;
   o->mg_wjac = 0.8;
   o->mg_wline = 0.7;

@@ -14,6 +14,7 @@ int apply_num_blocks(int64_t nx, int64_t ny);
 namespace {
 
 constexpr int kVecThreads = 256;
+constexpr int kScalThreads = 1024;  // one-CTA scalar kernels: the apply kernel leaves up to 32768 per-CTA partials
 
 __global__ void __launch_bounds__(kVecThreads)
 k_init(int64_t N, const c128* __restrict__ b, c128* __restrict__ x, c128* __restrict__ r, c128* __restrict__ rhat,
@@ -45,7 +46,7 @@ k_restart(int64_t N, const c128* __restrict__ b, const c128* __restrict__ t, c12
 // mode 0: fresh start (sets bnorm2); mode 1: restart (keeps bnorm2, tol2, iter); mode 2: true-residual probe (rr only)
 __global__ void k_scal_init(const c128* __restrict__ partials, int nb, KScal* sc, double tol, int mode) {
   double res[4];
-  final_reduce<kVecThreads, 4>(reinterpret_cast<const double*>(partials), nb, res);
+  final_reduce<kScalThreads, 4>(reinterpret_cast<const double*>(partials), nb, res);
   if (threadIdx.x == 0) {
     const double rr = res[2];
     if (mode == 2) { sc->rr = rr; return; }
@@ -106,7 +107,7 @@ __device__ __forceinline__ bool finite2(c128 a) { return isfinite(a.x) && isfini
 __global__ void k_scal_alpha(const c128* __restrict__ partials, int nb, KScal* sc) {
   if (sc->done) return;
   double res[2];
-  final_reduce<kVecThreads, 2>(reinterpret_cast<const double*>(partials), nb, res);
+  final_reduce<kScalThreads, 2>(reinterpret_cast<const double*>(partials), nb, res);
   if (threadIdx.x == 0) {
     const c128 rhv(res[0], res[1]);
     if (!finite2(rhv) || norm2(rhv) == 0.0) { sc->breakdown = 1; sc->done = 1; return; }
@@ -118,7 +119,7 @@ __global__ void k_scal_alpha(const c128* __restrict__ partials, int nb, KScal* s
 __global__ void k_scal_omega(const c128* __restrict__ partials, int nb, KScal* sc) {
   if (sc->done) return;
   double res[4];
-  final_reduce<kVecThreads, 4>(reinterpret_cast<const double*>(partials), nb, res);
+  final_reduce<kScalThreads, 4>(reinterpret_cast<const double*>(partials), nb, res);
   if (threadIdx.x == 0) {
     const double tt = res[2];
     if (!(tt > 0.0) || !isfinite(tt)) { sc->omega = c128(0.0, 0.0); }
@@ -130,7 +131,7 @@ __global__ void k_scal_omega(const c128* __restrict__ partials, int nb, KScal* s
 __global__ void k_scal_rho(const c128* __restrict__ partials, int nb, KScal* sc, double* __restrict__ hist, int hist_len) {
   if (sc->done) return;
   double res[4];
-  final_reduce<kVecThreads, 4>(reinterpret_cast<const double*>(partials), nb, res);
+  final_reduce<kScalThreads, 4>(reinterpret_cast<const double*>(partials), nb, res);
   if (threadIdx.x == 0) {
     const c128 rho_new(res[0], res[1]);
     const double rr = res[2];
@@ -219,7 +220,7 @@ static int bicgstab_loop(fdfd_ctx* ctx, KrylovWork& W, const KrylovOps& ops, con
   const bool use_graph = o.use_graph && st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
 
   k_init<<<nvb, kVecThreads, 0, st>>>(N, W.b.p, W.x.p, W.r.p, W.rhat.p, W.p.p, W.v.p, W.partials.p); KLAUNCH(ctx);
-  k_scal_init<<<1, kVecThreads, 0, st>>>(W.partials.p, nvb, sc, o.tol, 0); KLAUNCH(ctx);
+  k_scal_init<<<1, kScalThreads, 0, st>>>(W.partials.p, nvb, sc, o.tol, 0); KLAUNCH(ctx);
   CUDA_TRY(ctx, cudaGetLastError());
 
   int restarts = 0, flag = FDFD_OK;
@@ -237,14 +238,14 @@ static int bicgstab_loop(fdfd_ctx* ctx, KrylovWork& W, const KrylovOps& ops, con
         FDFD_TRY(ops.precond(true, &ph));
         DotSpec d1; d1.ndot = 1; d1.d0 = W.rhat.p; d1.partials = W.partials.p; d1.done = &sc->done;
         FDFD_TRY(ops.apply(ph, sizeof(TP) == sizeof(c64), W.v.p, d1));
-        k_scal_alpha<<<1, kVecThreads, 0, st>>>(W.partials.p, nab, sc); KLAUNCH(ctx);
+        k_scal_alpha<<<1, kScalThreads, 0, st>>>(W.partials.p, nab, sc); KLAUNCH(ctx);
         k_s_update<TP><<<nvb, kVecThreads, 0, st>>>(N, sc, W.r.p, W.v.p, W.s.p, prhs, fscale); KLAUNCH(ctx);
         FDFD_TRY(ops.precond(false, &sh));
         DotSpec d2; d2.ndot = 2; d2.d0 = W.s.p; d2.partials = W.partials.p; d2.done = &sc->done;
         FDFD_TRY(ops.apply(sh, sizeof(TP) == sizeof(c64), W.t.p, d2));
-        k_scal_omega<<<1, kVecThreads, 0, st>>>(W.partials.p, nab, sc); KLAUNCH(ctx);
+        k_scal_omega<<<1, kScalThreads, 0, st>>>(W.partials.p, nab, sc); KLAUNCH(ctx);
         k_xr_update<TP><<<nvb, kVecThreads, 0, st>>>(N, sc, W.x.p, (const TP*)ph, (const TP*)sh, W.s.p, W.t.p, W.r.p, W.rhat.p, W.partials.p); KLAUNCH(ctx);
-        k_scal_rho<<<1, kVecThreads, 0, st>>>(W.partials.p, nvb, sc, W.hist.p, hist_len); KLAUNCH(ctx);
+        k_scal_rho<<<1, kScalThreads, 0, st>>>(W.partials.p, nvb, sc, W.hist.p, hist_len); KLAUNCH(ctx);
         return FDFD_OK;
       };
       if (!use_graph) { FDFD_TRY(one_iteration()); continue; }
@@ -286,7 +287,7 @@ static int bicgstab_loop(fdfd_ctx* ctx, KrylovWork& W, const KrylovOps& ops, con
     DotSpec d0;
     FDFD_TRY(ops.apply(W.x.p, false, W.t.p, d0));
     k_true_resid<<<nvb, kVecThreads, 0, st>>>(N, W.b.p, W.t.p, W.partials.p); KLAUNCH(ctx);
-    k_scal_init<<<1, kVecThreads, 0, st>>>(W.partials.p, nvb, sc, o.tol, 2); KLAUNCH(ctx);
+    k_scal_init<<<1, kScalThreads, 0, st>>>(W.partials.p, nvb, sc, o.tol, 2); KLAUNCH(ctx);
     CUDA_TRY(ctx, cudaMemcpyAsync(W.h_scal, sc, sizeof(KScal), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     true_rel = std::sqrt(W.h_scal->rr / W.h_scal->bnorm2);
@@ -298,7 +299,7 @@ static int bicgstab_loop(fdfd_ctx* ctx, KrylovWork& W, const KrylovOps& ops, con
     // ---- restart from the current x (cures breakdown and recurrence drift)
     ++restarts;
     k_restart<<<nvb, kVecThreads, 0, st>>>(N, W.b.p, W.t.p, W.r.p, W.rhat.p, W.p.p, W.v.p, W.partials.p); KLAUNCH(ctx);
-    k_scal_init<<<1, kVecThreads, 0, st>>>(W.partials.p, nvb, sc, o.tol, 1); KLAUNCH(ctx);
+    k_scal_init<<<1, kScalThreads, 0, st>>>(W.partials.p, nvb, sc, o.tol, 1); KLAUNCH(ctx);
   }
   info->iters = W.h_scal->iter;
   info->relres = true_rel;

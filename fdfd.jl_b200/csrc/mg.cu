@@ -292,6 +292,148 @@ k_smooth2(OpView<T> op, const cplx<T>* __restrict__ u, const cplx<T>* __restrict
   }
 }
 
+// ---- shared-memory tiled variants for the bandwidth-bound fine levels ------------------------------------
+// 32-bit index arithmetic throughout (a level never exceeds 2^31 points); the 64-bit version was issue bound.
+// k_smooth2_tile: the (optionally coarse-corrected) iterate of a TX x TY tile plus a one-point halo is staged in
+// shared memory once (the untiled kernel evaluates the interpolation 5x per point), then residual / Jacobi /
+// strip capture run from the tile.  HBM traffic: u 8 + f 8 + mass 8 + out 8 B per point (fp32).
+constexpr int kTX = 64, kTY = 16, kTileThreads = 256;
+
+template <typename T, bool PROLONG>
+__device__ __forceinline__ cplx<T> iterate32(const cplx<T>* __restrict__ u, const ProlongView<T>& pv, int nx, int ny, int ix, int iy) {
+  cplx<T> v = u[ix + nx * iy];
+  if (PROLONG) {
+    const int nxc = (int)pv.nxc, nyc = (int)pv.nyc;
+    const int I0 = ix >> 1, J0 = iy >> 1;
+    const bool ox = ix & 1, oy = iy & 1;
+    const int I1 = ox ? (I0 + 1 == nxc ? 0 : I0 + 1) : I0;
+    const int J1 = oy ? (J0 + 1 == nyc ? 0 : J0 + 1) : J0;
+    const cplx<T>* r0 = pv.uc + nxc * J0;
+    cplx<T> lo = r0[I0];
+    if (ox) lo = pv.pwx[ix] * lo + pv.pwx[nx + ix] * r0[I1];
+    if (oy) {
+      const cplx<T>* r1 = pv.uc + nxc * J1;
+      cplx<T> hi = r1[I0];
+      if (ox) hi = pv.pwx[ix] * hi + pv.pwx[nx + ix] * r1[I1];
+      lo = pv.pwy[iy] * lo + pv.pwy[ny + iy] * hi;
+    }
+    v += lo;
+  }
+  return v;
+}
+
+template <typename T, bool TE, bool PROLONG>
+__global__ void __launch_bounds__(kTileThreads)
+k_smooth2_tile(OpView<T> op, const cplx<T>* __restrict__ u, const cplx<T>* __restrict__ f, cplx<T>* __restrict__ out,
+               cplx<T>* __restrict__ rxs, cplx<T>* __restrict__ rys, int npx, int npy, T wj, ProlongView<T> pv,
+               const int* __restrict__ done) {
+  if (done && *done) return;
+  __shared__ cplx<T> tile[(kTY + 2) * (kTX + 2)];
+  const int nx = (int)op.nx, ny = (int)op.ny;
+  const int x0 = blockIdx.x * kTX, y0 = blockIdx.y * kTY;
+  for (int idx = threadIdx.x; idx < (kTX + 2) * (kTY + 2); idx += kTileThreads) {
+    const int lx = idx % (kTX + 2), ly = idx / (kTX + 2);
+    int gx = x0 + lx - 1, gy = y0 + ly - 1;
+    if (gx > nx || gy > ny) continue;  // beyond the wrap halo of a partial tile: never read
+    gx = gx < 0 ? nx - 1 : (gx >= nx ? gx - nx : gx);
+    gy = gy < 0 ? ny - 1 : (gy >= ny ? gy - ny : gy);
+    tile[idx] = iterate32<T, PROLONG>(u, pv, nx, ny, gx, gy);
+  }
+  __syncthreads();
+  const int lx = threadIdx.x % kTX;
+  const int ix = x0 + lx;
+  if (ix >= nx) return;
+  const bool xs = in_strip(ix, nx, npx);
+  const int ixp = ix + 1 == nx ? 0 : ix + 1;
+  const cplx<T> cW = op.cxm[ix], cE = op.cxp[ix];
+#pragma unroll
+  for (int k = 0; k < kTY / (kTileThreads / kTX); ++k) {
+    const int ly = threadIdx.x / kTX + k * (kTileThreads / kTX);
+    const int iy = y0 + ly;
+    if (iy >= ny) break;
+    const int n = ix + nx * iy;
+    const bool ys = in_strip(iy, ny, npy);
+    cplx<T> W = cW, E = cE, S = op.cym[iy], Nn = op.cyp[iy], m;
+    if (TE) {
+      const int iyp = iy + 1 == ny ? 0 : iy + 1;
+      W = W * op.gx[n]; E = E * op.gx[ixp + nx * iy]; S = S * op.gy[n]; Nn = Nn * op.gy[ix + nx * iyp];
+      m = op.mass_const;
+    } else m = op.mass[n];
+    const cplx<T> C = m - W - E - S - Nn;
+    const cplx<T>* t = tile + (ly + 1) * (kTX + 2) + (lx + 1);
+    const cplx<T> u0 = t[0];
+    cplx<T> res = f[n];
+    res -= C * u0; res -= W * t[-1]; res -= E * t[1]; res -= S * t[-(kTX + 2)]; res -= Nn * t[kTX + 2];
+    if (xs) rxs[(int)strip_line(ix, nx, npx) * ny + iy] = res;
+    if (ys) rys[(int)strip_line(iy, ny, npy) * nx + ix] = res;
+    out[n] = (xs || ys) ? u0 : u0 + wj * cdiv(res, C);
+  }
+}
+
+// k_restrict_tile: residual of a (2 CX + 1) x (2 CY + 1) fine patch computed once into shared memory, then the
+// CX x CY coarse points of the tile take their 3 x 3 weighted sums.  HBM traffic: u 8 + f 8 + mass 8 B per fine
+// point + 2 B write (fp32) instead of 2.25x recomputation with stride-2 access.
+constexpr int kCX = 32, kCY = 8;
+constexpr int kRW = 2 * kCX + 1, kRH = 2 * kCY + 1;   // residual patch
+constexpr int kUW = kRW + 2, kUH = kRH + 2;           // iterate patch
+
+__device__ __forceinline__ int wrap32(int i, int n) {  // cheap for |i - [0,n)| < n, correct for tiny levels too
+  while (i < 0) i += n;
+  while (i >= n) i -= n;
+  return i;
+}
+
+template <typename T, bool TE>
+__global__ void __launch_bounds__(kTileThreads)
+k_restrict_tile(OpView<T> op, const cplx<T>* __restrict__ u, const cplx<T>* __restrict__ f, int64_t nxc64, int64_t nyc64,
+                const cplx<T>* __restrict__ rx, const cplx<T>* __restrict__ ry, cplx<T>* __restrict__ fc,
+                const int* __restrict__ done) {
+  if (done && *done) return;
+  __shared__ cplx<T> su[kUW * kUH];
+  __shared__ cplx<T> sr[kRW * kRH];
+  __shared__ int sgx[kUW], sgy[kUH];
+  const int nx = (int)op.nx, ny = (int)op.ny, nxc = (int)nxc64, nyc = (int)nyc64;
+  const int I0 = blockIdx.x * kCX, J0 = blockIdx.y * kCY;
+  // fine index of iterate-patch slot (lx,ly): 2 I0 - 2 + lx, wrapped (plain modulo: slots stay periodic neighbours)
+  const int fx0 = 2 * I0 - 2, fy0 = 2 * J0 - 2;
+  if (threadIdx.x < kUW) sgx[threadIdx.x] = wrap32(fx0 + threadIdx.x, nx);
+  else if (threadIdx.x >= 128 && threadIdx.x < 128 + kUH) sgy[threadIdx.x - 128] = wrap32(fy0 + (threadIdx.x - 128), ny);
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < kUW * kUH; idx += kTileThreads) {
+    const int lx = idx % kUW, ly = idx / kUW;
+    su[idx] = u[sgx[lx] + nx * sgy[ly]];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < kRW * kRH; idx += kTileThreads) {
+    const int lx = idx % kRW, ly = idx / kRW;
+    const int ix = sgx[lx + 1], iy = sgy[ly + 1];
+    const int n = ix + nx * iy;
+    cplx<T> W = op.cxm[ix], E = op.cxp[ix], S = op.cym[iy], Nn = op.cyp[iy], m;
+    if (TE) {
+      const int ixp = ix + 1 == nx ? 0 : ix + 1, iyp = iy + 1 == ny ? 0 : iy + 1;
+      W = W * op.gx[n]; E = E * op.gx[ixp + nx * iy]; S = S * op.gy[n]; Nn = Nn * op.gy[ix + nx * iyp];
+      m = op.mass_const;
+    } else m = op.mass[n];
+    const cplx<T> C = m - W - E - S - Nn;
+    const cplx<T>* t = su + (ly + 1) * kUW + (lx + 1);
+    cplx<T> res = f[n];
+    res -= C * t[0]; res -= W * t[-1]; res -= E * t[1]; res -= S * t[-kUW]; res -= Nn * t[kUW];
+    sr[idx] = res;
+  }
+  __syncthreads();
+  const int ci = threadIdx.x % kCX, cj = threadIdx.x / kCX;
+  const int I = I0 + ci, J = J0 + cj;
+  if (I >= nxc || J >= nyc) return;
+  cplx<T> acc(T(0), T(0));
+#pragma unroll
+  for (int b = 0; b < 3; ++b) {
+    const cplx<T> wy = ry[3 * J + b];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) acc += (rx[3 * I + a] * wy) * sr[(2 * cj + b) * kRW + (2 * ci + a)];
+  }
+  fc[I + nxc * J] = acc;
+}
+
 template <typename T>
 __global__ void k_lines2(int64_t nx, int64_t ny, int npx, int npy, int Ky, int Kx, const cplx<T>* __restrict__ mult_y,
                          const cplx<T>* __restrict__ mult_x, const cplx<T>* __restrict__ rxs, const cplx<T>* __restrict__ rys,
@@ -642,10 +784,13 @@ template <typename T> int Multigrid<T>::smooth(int l, bool zero, bool prolong) {
   cplx<T>* out = zero ? L.u.p : L.tmp.p;
   ProlongView<T> pv{0, 0, nullptr, nullptr, nullptr};
   if (prolong) { MGLevel<T>& C = lv[l + 1]; pv = ProlongView<T>{C.nx, C.ny, L.pw.p, L.pw.p + 2 * L.nx, C.u.p}; }
+  dim3 tgrid((unsigned)((L.nx + kTX - 1) / kTX), (unsigned)((L.ny + kTY - 1) / kTY));
 #define SM2(TEV, ZV, PV) k_smooth2<T, TEV, ZV, PV><<<grid, kMgThreads, 0, ctx->stream>>>(op, L.u.p, L.f.p, out, L.rxs.p, L.rys.p, L.npx, L.npy, wj, pv, done)
-  if (te) { if (zero) SM2(true, true, false); else if (prolong) SM2(true, false, true); else SM2(true, false, false); }
-  else    { if (zero) SM2(false, true, false); else if (prolong) SM2(false, false, true); else SM2(false, false, false); }
+#define SMT(TEV, PV) k_smooth2_tile<T, TEV, PV><<<tgrid, kTileThreads, 0, ctx->stream>>>(op, L.u.p, L.f.p, out, L.rxs.p, L.rys.p, L.npx, L.npy, wj, pv, done)
+  if (te) { if (zero) SM2(true, true, false); else if (prolong) SMT(true, true); else SMT(true, false); }
+  else    { if (zero) SM2(false, true, false); else if (prolong) SMT(false, true); else SMT(false, false); }
 #undef SM2
+#undef SMT
   KLAUNCH(ctx);
   if (!zero) std::swap(L.u.p, L.tmp.p);
   const int nlines = 2 * L.npx + 2 * L.npy;
@@ -672,9 +817,9 @@ template <typename T> int Multigrid<T>::cycle(int l, bool zero, int kind) {
   for (int s = 0; s < std::max(1, prm.nu1); ++s) FDFD_TRY(smooth(l, zero && s == 0));
   MGLevel<T>& C = lv[l + 1];
   {
-    dim3 grid((unsigned)((C.nx + 127) / 128), (unsigned)C.ny);
-    if (te) k_resid_restrict<T, true><<<grid, 128, 0, ctx->stream>>>(L.view(), L.u.p, L.f.p, C.nx, C.ny, L.rw.p, L.rw.p + 3 * C.nx, C.f.p, done);
-    else k_resid_restrict<T, false><<<grid, 128, 0, ctx->stream>>>(L.view(), L.u.p, L.f.p, C.nx, C.ny, L.rw.p, L.rw.p + 3 * C.nx, C.f.p, done);
+    dim3 grid((unsigned)((C.nx + kCX - 1) / kCX), (unsigned)((C.ny + kCY - 1) / kCY));
+    if (te) k_restrict_tile<T, true><<<grid, kTileThreads, 0, ctx->stream>>>(L.view(), L.u.p, L.f.p, C.nx, C.ny, L.rw.p, L.rw.p + 3 * C.nx, C.f.p, done);
+    else k_restrict_tile<T, false><<<grid, kTileThreads, 0, ctx->stream>>>(L.view(), L.u.p, L.f.p, C.nx, C.ny, L.rw.p, L.rw.p + 3 * C.nx, C.f.p, done);
     KLAUNCH(ctx);
   }
   if (kind == 2 && l < prm.wdepth) {

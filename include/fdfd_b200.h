@@ -76,7 +76,7 @@ typedef struct {
   int32_t mg_cycle;      /* FDFD_CYCLE_* (default W, truncated at mg_wdepth) */
   int32_t mg_wdepth;     /* levels [0,wdepth) recurse twice in a W cycle (default 2) */
   int32_t mg_nu1, mg_nu2;/* pre/post smoothing sweeps (default 1,1) */
-  int32_t mg_coarse_sweeps; /* sweeps on the coarsest level (default 4) */
+  int32_t mg_coarse_sweeps; /* sweeps on the coarsest level (default 2) */
   double  mg_beta;       /* complex shift: M = L + (1 - i*beta) w^2 eps (default 0.5) */
   double  mg_wjac;       /* point-Jacobi damping (default 0.8) */
   double  mg_wline;      /* PML line-relaxation damping (default 0.7) */
@@ -174,6 +174,9 @@ int fdfd_problem_get_solution(fdfd_problem* p, fdfd_c128* x);             /* (Nx
 int fdfd_problem_get_fields(fdfd_problem* p, int forward_h, fdfd_c128* fields); /* (Nx,Ny,3) */
 /* timed loop of nrep matrix-free applies on resident data; ms_per_apply from CUDA events */
 int fdfd_problem_bench_apply(fdfd_problem* p, int nrep, double* ms_per_apply);
+/* relative residual history of the last solve: out[k] = ||r_k|| / ||b|| (recurrence residual), k = 0..n-1;
+ * returns the number of entries written through *written */
+int fdfd_problem_get_history(fdfd_problem* p, double* out, int n, int* written);
 /* one application of the preconditioner M^-1 to a resident vector (parity/debug hook) */
 int fdfd_problem_precond(fdfd_problem* p, const fdfd_c128* in, fdfd_c128* out);
 
