@@ -59,7 +59,8 @@ extern "C" int fdfd_problem_create(fdfd_ctx* ctx, const fdfd_grid_t* g, int pol,
   fdfd_problem* P = new fdfd_problem();
   P->ctx = ctx;
   if (opts) P->opts = *opts; else fdfd_default_opts(&P->opts);
-  ARG_CHECK(ctx, P->opts.solver == FDFD_SOLVER_BICGSTAB, "only FDFD_SOLVER_BICGSTAB is implemented in this build");
+  if (!(P->opts.solver == FDFD_SOLVER_BICGSTAB || P->opts.solver == FDFD_SOLVER_COCG)) { delete P; fdfd_set_error(ctx, "fdfd_problem_create: solver must be FDFD_SOLVER_BICGSTAB or FDFD_SOLVER_COCG"); return FDFD_ERR_ARG; }
+  if (P->opts.solver == FDFD_SOLVER_COCG && P->opts.precond == FDFD_PRECOND_MG) { delete P; fdfd_set_error(ctx, "fdfd_problem_create: COCG needs a symmetric preconditioner (FDFD_PRECOND_JACOBI or FDFD_PRECOND_NONE); the multigrid cycle is not symmetric"); return FDFD_ERR_ARG; }
   const double t0 = now_ms();
   int st = P->op.build(ctx, *g, pol, ordering, omega, eps_r);
   if (st != FDFD_OK) { delete P; return st; }
@@ -118,8 +119,8 @@ extern "C" int fdfd_problem_solve(fdfd_problem* P, fdfd_info_t* info) {
   std::memset(info, 0, sizeof(*info));
   CUDA_TRY(P->ctx, cudaSetDevice(P->ctx->device));
   const double t0 = now_ms();
-  KrylovOps ops = P->make_ops();
-  FDFD_TRY(krylov_bicgstab(P->ctx, P->w, ops, P->opts, info));
+  if (P->opts.solver == FDFD_SOLVER_COCG) { FDFD_TRY(krylov_cocg(P, info)); }
+  else { KrylovOps ops = P->make_ops(); FDFD_TRY(krylov_bicgstab(P->ctx, P->w, ops, P->opts, info)); }
   info->setup_ms = P->setup_ms;
   info->mg_levels = P->mgf ? P->mgf->levels() : (P->mgd ? P->mgd->levels() : 0);
   info->total_ms = now_ms() - t0;

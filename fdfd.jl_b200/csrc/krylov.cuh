@@ -63,4 +63,5 @@ struct fdfd_problem {
 };
 
 MGParams mg_params_from(const fdfd_solve_opts_t& o);
+int krylov_cocg(fdfd_problem* P, fdfd_info_t* info);
 int jacobi_apply(fdfd_ctx* ctx, const FineOp& op, const c128* in, c128* out, const int* done, int blocks);

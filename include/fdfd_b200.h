@@ -49,7 +49,8 @@ enum { FDFD_DXF = 0, FDFD_DXB = 1, FDFD_DYF = 2, FDFD_DYB = 3 };
 /* sparse formats: CSR (row pointers) or CSC (Julia SparseMatrixCSC: colptr,rowval,nzval) */
 enum { FDFD_CSR = 0, FDFD_CSC = 1 };
 /* Krylov solvers / preconditioners */
-enum { FDFD_SOLVER_BICGSTAB = 0, FDFD_SOLVER_COCG = 1, FDFD_SOLVER_GMRES = 2 };
+/* BICGSTAB: any preconditioner.  COCG: on the symmetrised system diag(sxf*syf) A, Jacobi or no preconditioner. */
+enum { FDFD_SOLVER_BICGSTAB = 0, FDFD_SOLVER_COCG = 1 };
 enum { FDFD_PRECOND_NONE = 0, FDFD_PRECOND_JACOBI = 1, FDFD_PRECOND_MG = 2 };
 enum { FDFD_MG_F32 = 0, FDFD_MG_F64 = 1 };
 enum { FDFD_CYCLE_V = 0, FDFD_CYCLE_F = 1, FDFD_CYCLE_W = 2 };

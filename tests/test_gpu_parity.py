@@ -192,3 +192,74 @@ def test_zero_source_and_bad_args(fdfd):
         fdfd.solve(fdfd.Device(bad, W200))
     with pytest.raises(fdfd.FdfdError):
         fdfd.apply_operator(g, 7, W200, d.eps_r, d.src)
+
+
+# ---- full-size configurations (BASELINE.json configs 2, 3): size-independent properties, no CPU oracle needed -----
+def _true_relres(fdfd, g, pol, omega, eps, x, b):
+    """residual recomputed OUTSIDE the solver with the fp64 stencil through the C ABI"""
+    r = b - fdfd.apply_operator(g, pol, omega, eps, x)
+    return np.linalg.norm(r) / np.linalg.norm(b)
+
+
+def test_config2_directional_coupler_fullsize(fdfd):
+    """2000x1000 TM directional coupler with a mode source (README figure): independent residual check, linearity in the
+    source, power conservation between the two output guides and the input (flux consumer, flux.jl:37-47)."""
+    from importlib import import_module
+    wl = import_module("fdfd_jl_b200.workloads")
+    d = wl.directional_coupler(fdfd)
+    g = d.grid
+    assert g.N == (2000, 1000)
+    f = fdfd.solve(d)
+    assert f.info["flag"] == 0 and f.info["relres"] <= RES_TOL
+    b = 1j * d.omega[0] * d.src
+    assert _true_relres(fdfd, g, fdfd.TM, d.omega[0], d.eps_r, f["Ez"], b) <= 2 * RES_TOL
+    # linearity: doubling the source doubles the field
+    d2 = fdfd.Device(g, d.omega[0]); d2.eps_r = d.eps_r; d2.src = 2 * d.src
+    f2 = fdfd.solve(d2)
+    assert rel(f2.data, 2 * f.data) <= 1e-8
+    # flux through a plane just after the source ~= flux through a plane before the right PML (lossless guides)
+    Lx = g.bounds[1][0]
+    pin = fdfd.flux_surface_integral(f, fdfd.Point(0.5, 0), np.inf, fdfd.XHAT)
+    pout = fdfd.flux_surface_integral(f, fdfd.Point(Lx - 0.3, 0), np.inf, fdfd.XHAT)
+    assert pin > 0 and abs(pout / pin - 1) < 0.05
+
+
+def test_config3_te_photonic_crystal_sweep(fdfd):
+    """TE photonic-crystal slab, a 3-frequency slice of the 64-frequency sweep at 512x512: every frequency converges and
+    passes the independent residual check."""
+    from importlib import import_module
+    wl = import_module("fdfd_jl_b200.workloads")
+    d = wl.photonic_crystal_slab(fdfd, 512, 512, nfreq=64)
+    d.omega = [d.omega[0], d.omega[31], d.omega[63]]
+    fs = fdfd.solve(d, fdfd.TE)
+    assert len(fs) == 3
+    for f, w in zip(fs, d.omega):
+        assert f.info["flag"] == 0 and f.info["relres"] <= RES_TOL
+        b = 1j * w * d.src
+        assert _true_relres(fdfd, d.grid, fdfd.TE, w, d.eps_r, f["Hz"], b) <= 2 * RES_TOL
+
+
+@pytest.mark.parametrize("precond", [0, 1])
+def test_cocg_option_small_vacuum(fdfd, precond):
+    """north_star's COCG + Jacobi option on the symmetrised system diag(sxf*syf) A: converges on a small vacuum dipole
+    (thousands of iterations; it is not the default) and matches the oracle."""
+    gargs = (0.06, [10, 10], [-3, 3], [-3, 3])  # 100 x 100
+    g, go = fdfd.Grid(*gargs), O.Grid2D(*gargs)
+    d = fdfd.Device(g, W200)
+    fdfd.setup_src(d, fdfd.Point(0, 0))
+    f = fdfd.solve(d, fdfd.TM, solver=fdfd._lib.SOLVER_COCG, precond=precond, maxit=60000, check_every=64)
+    assert f.info["flag"] == 0 and f.info["relres"] <= RES_TOL
+    fo = O.solve(_oracle_device(go, d), O.TM)
+    assert rel(f.data, fo["data"]) <= FIELD_TOL
+    with pytest.raises(fdfd.FdfdError):  # COCG + (non-symmetric) multigrid is refused
+        fdfd.solve(d, fdfd.TM, solver=fdfd._lib.SOLVER_COCG, precond=2)
+
+
+def test_jacobi_bicgstab_option(fdfd):
+    gargs = (0.06, [10, 10], [-3, 3], [-3, 3])
+    g, go = fdfd.Grid(*gargs), O.Grid2D(*gargs)
+    d = fdfd.Device(g, W200)
+    fdfd.setup_src(d, fdfd.Point(0, 0))
+    f = fdfd.solve(d, fdfd.TM, precond=1, maxit=100000, check_every=64)
+    assert f.info["flag"] == 0 and f.info["relres"] <= RES_TOL
+    assert rel(f.data, O.solve(_oracle_device(go, d), O.TM)["data"]) <= FIELD_TOL
