@@ -4,9 +4,11 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N ...            # the reference algorithm (sparse direct LU) on host cores
 
-One "step" = one complete driven solve of the synthetic 4096x4096 TM device: per-frequency operator
-setup (PML coefficients, multigrid hierarchy), the GPU-resident Krylov solve to ||b-Ax||/||b|| <= 1e-10 (checked
-with the fp64 operator) and H-field recovery.  `value` times that with eps_r/src resident in HBM; `e2e` times the
+One "step" = one call of the hot path, `solve(device, TM)` == fdfd_solve_driven, on the synthetic 4096x4096 TM
+device carrying a sweep of --sweep (default 4) frequencies: for each frequency the per-frequency operator
+setup (PML coefficients, multigrid hierarchy), the GPU-resident Krylov solve to ||b-Ax||/||b|| <= 1e-10 (checked with
+the fp64 operator) and H-field recovery; the library overlaps the frequencies on separate streams.  The metric counts
+solved (omega, source) right-hand sides per second.  `value` times that with eps_r/src resident in HBM; `e2e` times the
 public API call (`solve(device)`) with host buffers, H2D and D2H copies inside the timed region.  N > 1: one rank
 per GPU, each rank solves its own frequency of an omega sweep (no data-path collective): weak scaling.
 """
@@ -32,13 +34,14 @@ ALG_BYTES_PER_POINT = 48.0  # read x 16 + read w^2*eps 16 + write y 16 (complex1
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--grid", dest="n", type=int, default=4096, help="grid edge (cells); 4096 is the metric's configuration")
     ap.add_argument("--density", type=float, default=1.0 / 160.0, help="scatterers per um^2 of the synthetic map")
     ap.add_argument("--ref-grid", dest="ref_n", type=int, default=512, help="grid edge of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sweep", type=int, default=4, help="frequencies per GPU per step, solved concurrently (one stream each)")
     return ap.parse_args()
 
 
@@ -153,14 +156,16 @@ def metric_name(args):
 
 def workload_config(args):
     return {"workload": f"synthetic TM device {args.n}x{args.n} (dh=0.02um=lambda0/75, Npml=15, eps=12 waveguide + seeded eps 2..12.25 "
-                        f"cylinders/boxes at {args.density:.5f}/um^2, x-normal line source), one 200 THz-band frequency per rank, "
-                        f"solve to 1e-10 relative residual incl. per-frequency setup and H recovery",
+                        f"cylinders/boxes at {args.density:.5f}/um^2, x-normal line source); one step = a sweep of {args.sweep} frequencies "
+                        f"(200 THz + k*0.5 THz) per GPU solved concurrently, each to 1e-10 relative residual incl. per-frequency "
+                        f"setup and H recovery; value counts solved (omega,source) right-hand sides per second",
             "grid": [args.n, args.n], "solver": "BiCGSTAB + shifted-Laplacian multigrid (fp32) / fp64 operator",
-            "l2": "inputs larger than L2: one complex128 vector is 268 MB vs 126 MB L2", "parallelism": "omega sweep, one frequency per GPU"}
+            "l2": "inputs larger than L2: one complex128 vector is 268 MB vs 126 MB L2", "parallelism": f"omega sweep: {args.sweep} frequencies per GPU per step, disjoint frequencies per rank, no collective"}
 
 
 # ------------------------------------------------------------------------------------------------------------
 def b200_arm(args):
+    import ctypes as C
     import torch
     import torch.distributed as dist
     import fdfd_jl_b200 as fdfd
@@ -173,21 +178,25 @@ def b200_arm(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    stream = torch.cuda.Stream()  # the library launches on this stream, so torch CUDA events bracket its kernels
+    stream = torch.cuda.Stream()  # the library's main stream; worker streams of the sweep fork from the same device
     ctx = fdfd.Context(local, stream=stream.cuda_stream)
-    n = args.n
+    n, B = args.n, args.sweep
     N = n * n
 
     d = wl.synthetic_tm_device(fdfd, n, n, density=args.density)
-    omega = 2 * math.pi * (200e12 + 0.5e12 * rank)  # each rank owns one frequency of the sweep
     g = d.grid
-    # inputs resident in HBM (torch is plumbing: device memory + pinned host buffers)
+    gc = g.as_c()
+    # this rank's slice of the omega sweep: B frequencies, solved concurrently by the library (one stream each)
+    omegas = [2 * math.pi * (200e12 + 0.5e12 * (rank * B + k)) for k in range(B)]
+    wB = (C.c_double * B)(*omegas)
+    opts = fdfd.default_opts(concurrency=B)
+    # torch is plumbing: device memory and pinned host buffers
     eps_h = torch.from_numpy(np.asfortranarray(d.eps_r).ravel(order="F").copy()).pin_memory()
     src_h = torch.from_numpy(np.asfortranarray(d.src).ravel(order="F").copy()).pin_memory()
     eps_d = eps_h.cuda(non_blocking=True)
     src_d = src_h.cuda(non_blocking=True)
-    fields_d = torch.empty(3 * N, dtype=torch.complex128, device="cuda")
-    fields_h = torch.empty(3 * N, dtype=torch.complex128).pin_memory()
+    fields_d = torch.empty(B * 3 * N, dtype=torch.complex128, device="cuda")
+    fields_h = torch.empty(B * 3 * N, dtype=torch.complex128).pin_memory()
     torch.cuda.synchronize()
 
     def barrier():
@@ -196,37 +205,26 @@ def b200_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    infos = []
-
-    def step_resident():
-        P = fdfd.Problem(g, fdfd.TM, omega, eps_d.data_ptr(), ctx=ctx)
-        P.set_source(src_d.data_ptr())
-        info = P.solve()
-        P.fields(False, out=fields_d.data_ptr())
-        P.close()
-        return info
-
-    def step_e2e():
-        import ctypes as C
-        o = fdfd.default_opts()
-        gc = g.as_c()
-        info = fdfd.Info()
-        w = (C.c_double * 1)(omega)
-        code = fdfd.lib().fdfd_solve_driven(ctx.handle, C.byref(gc), fdfd.TM, 1, w, fdfd.ptr(eps_h.data_ptr()), fdfd.ptr(src_h.data_ptr()), 0,
-                                            C.byref(o), fdfd.ptr(fields_h.data_ptr()), C.byref(info))
+    def sweep(eps_ptr, src_ptr, out_ptr):
+        """the hot path through the C ABI: fdfd_solve_driven == solve(d::Device, pol) for B frequencies"""
+        infos = (fdfd.Info * B)()
+        code = fdfd.lib().fdfd_solve_driven(ctx.handle, C.byref(gc), fdfd.TM, B, wB, fdfd.ptr(eps_ptr), fdfd.ptr(src_ptr), 0,
+                                            C.byref(opts), fdfd.ptr(out_ptr), infos)
         fdfd.check(code, ctx.handle)
-        return info.asdict()
+        return [i.asdict() for i in infos]
 
-    # ---- device-resident timing: CUDA events on the launching stream, barrier + synchronize on both sides
+    # ---- device-resident timing: CUDA events on the library's stream, barrier + synchronize on both sides
+    infos = []
     for _ in range(args.warmup):
-        step_resident()
+        sweep(eps_d.data_ptr(), src_d.data_ptr(), fields_d.data_ptr())
     barrier()
     l0 = ctx.launch_count()
     with ClockSampler(local) as clk:
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(args.steps):
-            infos.append(step_resident())
+            infos += sweep(eps_d.data_ptr(), src_d.data_ptr(), fields_d.data_ptr())
+            stream.synchronize()
         e1.record(stream)
         torch.cuda.synchronize()
         t_res = e0.elapsed_time(e1) * 1e-3
@@ -237,14 +235,15 @@ def b200_arm(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_max = float(tt.item())
 
-    # ---- end-to-end timing (host buffers in, fields out)
+    # ---- end-to-end: the same call with pinned HOST buffers (H2D of eps_r/src, D2H of the B (Nx,Ny,3) fields inside)
     e2e_steps = max(1, min(args.steps, 2))
-    step_e2e()
+    sweep(eps_h.data_ptr(), src_h.data_ptr(), fields_h.data_ptr())
     barrier()
     e2 = torch.cuda.Event(enable_timing=True); e3 = torch.cuda.Event(enable_timing=True)
     e2.record(stream)
     for _ in range(e2e_steps):
-        step_e2e()
+        sweep(eps_h.data_ptr(), src_h.data_ptr(), fields_h.data_ptr())
+        stream.synchronize()
     e3.record(stream)
     torch.cuda.synchronize()
     te = torch.tensor([e2.elapsed_time(e3) * 1e-3], dtype=torch.float64, device="cuda")
@@ -253,7 +252,7 @@ def b200_arm(args):
     t_e2e = float(te.item())
 
     # ---- roofline of the stencil apply kernel, timed live with CUDA events on the launching stream
-    P = fdfd.Problem(g, fdfd.TM, omega, eps_d.data_ptr(), ctx=ctx, precond=0)
+    P = fdfd.Problem(g, fdfd.TM, omegas[0], eps_d.data_ptr(), ctx=ctx, precond=0)
     ms_apply = P.bench_apply(200)
     P.close()
     peak, peak_src = measured_peak()
@@ -264,16 +263,16 @@ def b200_arm(args):
     if world > 1:
         dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     if rank == 0:
-        value = world * args.steps / t_max
+        value = world * B * args.steps / t_max
         line = {"metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": t_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "c128", "data": "synthetic", "config": workload_config(args),
                 "converged": bool(flags.item()),
-                "solve": {"iters": [i["iters"] for i in infos], "relres": [i["relres"] for i in infos],
-                          "krylov_ms": [i["solve_ms"] for i in infos], "setup_ms": [i["setup_ms"] for i in infos],
+                "solve": {"solves_per_step_per_gpu": B, "iters": [i["iters"] for i in infos], "relres_max": max(i["relres"] for i in infos),
+                          "krylov_ms": [round(i["solve_ms"], 1) for i in infos], "setup_ms": [round(i["setup_ms"], 1) for i in infos],
                           "mg_levels": infos[0]["mg_levels"]},
-                "e2e": {"value": world * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * N * 16, "d2h_bytes_per_step": 3 * N * 16,
-                        "steps": e2e_steps},
+                "e2e": {"value": world * B * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * N * 16,
+                        "d2h_bytes_per_step": B * 3 * N * 16, "steps": e2e_steps},
                 "gpu_launches": int(launches),
                 "clocks": clk.summary(),
                 "roofline": {"kernel": "k_apply (matrix-free complex128 Yee stencil, TM)", "bound": "hbm", "achieved": achieved, "peak": peak,
@@ -289,9 +288,8 @@ def b200_arm(args):
                                     "sample": f"oracle (SciPy SuperLU direct solve, stand-in for Julia \\/UMFPACK) on the same device at "
                                               f"{args.ref_n}^2: {t_cpu:.2f} s; scaled to {n}^2 by t ~ N^{expo:.2f} (BASELINE.md §3)",
                                     "sample_seconds_per_solve": t_cpu}
-        # ncu traffic of the same kernel, if a summary has been committed
         prof = os.path.join(ROOT, "profiles", "r01_k_apply_traffic.json")
-        if os.path.exists(prof):
+        if os.path.exists(prof) and n == 4096:
             try:
                 line["roofline"]["traffic"] = json.load(open(prof))["dram_bytes_per_launch"]
             except Exception:

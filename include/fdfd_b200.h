@@ -86,6 +86,8 @@ typedef struct {
   double  mg_shift_growth; /* level/space dependent shift: beta_eff = max(beta, growth * Re(k^2 h_l^2)) (default 0 = off) */
   int32_t mg_max_levels; /* cap on hierarchy depth (default 32) */
   int32_t use_graph;     /* replay the iteration as a CUDA graph (default 1) */
+  int32_t concurrency;   /* fdfd_solve_driven: frequencies solved concurrently on separate streams (default 4) */
+  int32_t reserved;
 } fdfd_solve_opts_t;
 
 typedef struct {

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol(fdfd):
 
 def test_struct_layouts_match_header(fdfd):
     assert ctypes.sizeof(fdfd.GridT) == 4 * 8 + 5 * 8
-    assert ctypes.sizeof(fdfd.SolveOpts) == 96
+    assert ctypes.sizeof(fdfd.SolveOpts) == 104
     assert ctypes.sizeof(fdfd.Info) == 56
     o = fdfd.default_opts()
     assert o.tol == 1e-10 and o.precond == fdfd._lib.PRECOND_MG and o.mg_beta == 0.5
