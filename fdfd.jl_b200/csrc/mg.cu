@@ -331,7 +331,7 @@ k_smooth2_tile(OpView<T> op, const cplx<T>* __restrict__ u, const cplx<T>* __res
   __shared__ cplx<T> tile[(kTY + 2) * (kTX + 2)];
   const int nx = (int)op.nx, ny = (int)op.ny;
   const int x0 = blockIdx.x * kTX, y0 = blockIdx.y * kTY;
-  for (int idx = threadIdx.x; idx < (kTX + 2) * (kTY + 2); idx += kTileThreads) {
+  for (int idx = threadIdx.x; idx < (kTX + 2) * (kTY + 2); idx += kTileThreads) {  // 1-D: every pass is full width
     const int lx = idx % (kTX + 2), ly = idx / (kTX + 2);
     int gx = x0 + lx - 1, gy = y0 + ly - 1;
     if (gx > nx || gy > ny) continue;  // beyond the wrap halo of a partial tile: never read
@@ -392,14 +392,20 @@ k_restrict_tile(OpView<T> op, const cplx<T>* __restrict__ u, const cplx<T>* __re
   __shared__ cplx<T> su[kUW * kUH];
   __shared__ cplx<T> sr[kRW * kRH];
   __shared__ int sgx[kUW], sgy[kUH];
+  __shared__ cplx<T> scxm[kUW], scxp[kUW], scym[kUH], scyp[kUH];  // 1-D coefficient slices of the patch (L1 relief)
   const int nx = (int)op.nx, ny = (int)op.ny, nxc = (int)nxc64, nyc = (int)nyc64;
   const int I0 = blockIdx.x * kCX, J0 = blockIdx.y * kCY;
   // fine index of iterate-patch slot (lx,ly): 2 I0 - 2 + lx, wrapped (plain modulo: slots stay periodic neighbours)
   const int fx0 = 2 * I0 - 2, fy0 = 2 * J0 - 2;
-  if (threadIdx.x < kUW) sgx[threadIdx.x] = wrap32(fx0 + threadIdx.x, nx);
-  else if (threadIdx.x >= 128 && threadIdx.x < 128 + kUH) sgy[threadIdx.x - 128] = wrap32(fy0 + (threadIdx.x - 128), ny);
+  if (threadIdx.x < kUW) {
+    const int gx = wrap32(fx0 + threadIdx.x, nx);
+    sgx[threadIdx.x] = gx; scxm[threadIdx.x] = op.cxm[gx]; scxp[threadIdx.x] = op.cxp[gx];
+  } else if (threadIdx.x >= 128 && threadIdx.x < 128 + kUH) {
+    const int gy = wrap32(fy0 + (threadIdx.x - 128), ny);
+    sgy[threadIdx.x - 128] = gy; scym[threadIdx.x - 128] = op.cym[gy]; scyp[threadIdx.x - 128] = op.cyp[gy];
+  }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < kUW * kUH; idx += kTileThreads) {
+  for (int idx = threadIdx.x; idx < kUW * kUH; idx += kTileThreads) {  // 1-D: every pass is full width
     const int lx = idx % kUW, ly = idx / kUW;
     su[idx] = u[sgx[lx] + nx * sgy[ly]];
   }
@@ -408,7 +414,7 @@ k_restrict_tile(OpView<T> op, const cplx<T>* __restrict__ u, const cplx<T>* __re
     const int lx = idx % kRW, ly = idx / kRW;
     const int ix = sgx[lx + 1], iy = sgy[ly + 1];
     const int n = ix + nx * iy;
-    cplx<T> W = op.cxm[ix], E = op.cxp[ix], S = op.cym[iy], Nn = op.cyp[iy], m;
+    cplx<T> W = scxm[lx + 1], E = scxp[lx + 1], S = scym[ly + 1], Nn = scyp[ly + 1], m;
     if (TE) {
       const int ixp = ix + 1 == nx ? 0 : ix + 1, iyp = iy + 1 == ny ? 0 : iy + 1;
       W = W * op.gx[n]; E = E * op.gx[ixp + nx * iy]; S = S * op.gy[n]; Nn = Nn * op.gy[ix + nx * iyp];
@@ -441,8 +447,8 @@ __global__ void k_lines2(int64_t nx, int64_t ny, int npx, int npy, int Ky, int K
   if (done && *done) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const bool ymode = (int)blockIdx.x < 2 * npx;       // y-line of a strip column, else x-line of a strip row
-  const int64_t c = ymode ? blockIdx.x : blockIdx.x - 2 * npx;
-  const int64_t n = ymode ? ny : nx;
+  const int c = ymode ? blockIdx.x : blockIdx.x - 2 * npx;
+  const int n = (int)(ymode ? ny : nx);
   const int K = ymode ? Ky : Kx;
   const int64_t nmax = nx > ny ? nx : ny;
   cplx<T>* d0 = gscratch ? gscratch + (size_t)blockIdx.x * 2 * nmax : reinterpret_cast<cplx<T>*>(smem_raw);
@@ -451,24 +457,63 @@ __global__ void k_lines2(int64_t nx, int64_t ny, int npx, int npy, int Ky, int K
   const cplx<T>* alpha = mult + (size_t)c * (2 * K + 1) * n;
   const cplx<T>* gamma = alpha + (size_t)K * n;
   const cplx<T>* binv = gamma + (size_t)K * n;
-  const cplx<T>* rbuf = (ymode ? rxs : rys) + c * n;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) d0[i] = rbuf[i];
-  __syncthreads();
-  for (int k = 0; k < K; ++k) {
-    const int64_t s = (int64_t)1 << k;
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-      cplx<T> v = d0[i];
-      if (i >= s) v += alpha[(size_t)k * n + i] * d0[i - s];
-      if (i + s < n) v += gamma[(size_t)k * n + i] * d0[i + s];
-      d1[i] = v;
+  const cplx<T>* rbuf = (ymode ? rxs : rys) + (size_t)c * n;
+  constexpr int EPT = 4;  // elements per thread held in registers
+  const int nt = blockDim.x, tid = threadIdx.x;
+  for (int i = tid; i < n; i += nt) d0[i] = rbuf[i];
+  if (n <= EPT * nt) {
+    // the multipliers of step k+1 are fetched while step k runs out of shared memory: the PCR steps are otherwise a
+    // chain of (global-load latency + barrier) with nothing to overlap
+    cplx<T> a_cur[EPT], g_cur[EPT], a_nxt[EPT], g_nxt[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      const int i = tid + e * nt;
+      if (i < n && K > 0) { a_cur[e] = alpha[i]; g_cur[e] = gamma[i]; }
     }
     __syncthreads();
-    cplx<T>* t = d0; d0 = d1; d1 = t;
+    for (int k = 0; k < K; ++k) {
+      const int s = 1 << k;
+      if (k + 1 < K) {
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+          const int i = tid + e * nt;
+          if (i < n) { a_nxt[e] = alpha[(size_t)(k + 1) * n + i]; g_nxt[e] = gamma[(size_t)(k + 1) * n + i]; }
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        const int i = tid + e * nt;
+        if (i < n) {
+          cplx<T> v = d0[i];
+          if (i >= s) v += a_cur[e] * d0[i - s];
+          if (i + s < n) v += g_cur[e] * d0[i + s];
+          d1[i] = v;
+        }
+      }
+      __syncthreads();
+      cplx<T>* t = d0; d0 = d1; d1 = t;
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) { a_cur[e] = a_nxt[e]; g_cur[e] = g_nxt[e]; }
+    }
+  } else {
+    __syncthreads();
+    for (int k = 0; k < K; ++k) {
+      const int s = 1 << k;
+      for (int i = tid; i < n; i += nt) {
+        cplx<T> v = d0[i];
+        if (i >= s) v += alpha[(size_t)k * n + i] * d0[i - s];
+        if (i + s < n) v += gamma[(size_t)k * n + i] * d0[i + s];
+        d1[i] = v;
+      }
+      __syncthreads();
+      cplx<T>* t = d0; d0 = d1; d1 = t;
+    }
   }
-  const int64_t fixed = strip_index(c, ymode ? nx : ny, ymode ? npx : npy);
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+  const int fixed = (int)strip_index(c, ymode ? nx : ny, ymode ? npx : npy);
+  const int inx = (int)nx;
+  for (int i = tid; i < n; i += nt) {
     if (ymode && in_strip(i, ny, npy)) continue;  // corners belong to the x-lines
-    const int64_t idx = ymode ? fixed + nx * i : i + nx * fixed;
+    const int64_t idx = ymode ? (int64_t)fixed + (int64_t)inx * i : (int64_t)i + (int64_t)inx * fixed;
     out[idx] += wl * (d0[i] * binv[i]);
   }
 }
