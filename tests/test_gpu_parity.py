@@ -263,3 +263,9 @@ def test_jacobi_bicgstab_option(fdfd):
     f = fdfd.solve(d, fdfd.TM, precond=1, maxit=100000, check_every=64)
     assert f.info["flag"] == 0 and f.info["relres"] <= RES_TOL
     assert rel(f.data, O.solve(_oracle_device(go, d), O.TM)["data"]) <= FIELD_TOL
+
+
+def test_graft_entry_smoke():
+    """the driver's smoke(): one small solve on cuda:0 checked against the oracle"""
+    import __graft_entry__ as ge
+    ge.smoke()
