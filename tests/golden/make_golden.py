@@ -1,0 +1,55 @@
+"""Generates the committed golden fixtures of tests/golden/ from the CPU oracle (run in the build container):
+    python tests/golden/make_golden.py
+* notebook_example3.json -- the reference's only known-answer numbers (notebooks/Example_simulations.ipynb cells 21/23/25),
+  copied from the notebook outputs, plus the oracle's reproduction of them.
+* tm_small.npz / te_small.npz / mod_small.npz -- small seeded problems: inputs, CSR of the system matrix and the solved
+  (Nx,Ny,3) fields, so the GPU tests can also be checked against committed vectors."""
+import json
+import math
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import fdfd_oracle as O  # noqa: E402
+
+W = 2 * math.pi * 200e12
+
+
+def small(pol):
+    g = O.Grid2D(0.05, [6, 5], [0, 2.0], [0, 1.5])
+    d = O.Device(g, [W])
+    rng = np.random.default_rng(7)
+    d.eps_r = (1 + 11 * rng.random(g.size())).round(2) + 0j
+    d.src[10, 12] = 1j
+    A, b, _ = O.system_matrix(d, W, pol)
+    A.sort_indices()
+    f = O.solve(d, pol)
+    return dict(dh=0.05, npml=[6, 5], xr=[0, 2.0], yr=[0, 1.5], omega=W, eps_r=d.eps_r, src=d.src, indptr=A.indptr.astype(np.int64),
+                indices=A.indices.astype(np.int64), data=A.data, fields=f["data"])
+
+
+def modulated_small():
+    g = O.Grid2D(0.04, [8, 8], [0, 3.0], [-1.0, 1.0])
+    d = O.ModulatedDevice(g, [2 * math.pi * 1.939e14], Omega=4.541e14, nsidebands=1)
+    a = 0.2202
+    O.mask_values(d.eps_r, g, lambda x, y: -a / 2 <= y <= a / 2, 12.25)
+    O.mask_values(d.deps_r, g, lambda x, y: (0.6 <= x <= 2.4) and (-a / 2 <= y <= 0), lambda x, y: np.exp(1j * 2.9263 * x))
+    d.src[12, :] = 1j
+    f = O.solve_modulated(d)[0]
+    return dict(dh=0.04, npml=[8, 8], xr=[0, 3.0], yr=[-1.0, 1.0], omega=d.omega[0], Omega=d.Omega, eps_r=d.eps_r, deps_r=d.deps_r,
+                src=d.src, fields=np.stack([x["data"] for x in f], axis=3))
+
+
+if __name__ == "__main__":
+    np.savez_compressed(os.path.join(HERE, "tm_small.npz"), **small(O.TM))
+    np.savez_compressed(os.path.join(HERE, "te_small.npz"), **small(O.TE))
+    np.savez_compressed(os.path.join(HERE, "mod_small.npz"), **modulated_small())
+    nb = {"source": "reference notebooks/Example_simulations.ipynb, Example 3 (cells 17-25)",
+          "Nin_cell21": 1.3625216010889075e-20, "Nout_cell23": 1.3618731014650896e-20, "ratio_cell25": 0.9995240445191477,
+          "oracle_Nin": 1.3625216010888627e-20, "oracle_Nout": 1.3618731014650806e-20,
+          "oracle_rel_err": [-3.3e-14, -6.7e-15]}
+    json.dump(nb, open(os.path.join(HERE, "notebook_example3.json"), "w"), indent=1)
+    print("wrote", os.listdir(HERE))
