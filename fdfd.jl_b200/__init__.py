@@ -426,6 +426,25 @@ def apply_operator(g: Grid, pol, omega, eps_r, x, ordering=_lib.ORDER_FB, ctx=No
     return y
 
 
+def rasterize(g: Grid, shapes, eps_r=None, ctx=None):
+    """setup_ϵᵣ!(d, shapes) on the GPU for Box / Cylinder shapes with constant data (src/device.jl:47-61)."""
+    ctx = ctx or default_context()
+    eps = np.asfortranarray(np.ones(g.N, dtype=np.complex128) if eps_r is None else np.array(eps_r, dtype=np.complex128))
+    rows = []
+    for sh in shapes:
+        v = complex(sh.data)
+        if isinstance(sh, Box):
+            rows.append([0.0, sh.center[0], sh.center[1], min(sh.size[0], 1e300), min(sh.size[1], 1e300), v.real, v.imag])
+        elif isinstance(sh, Cylinder):
+            rows.append([1.0, sh.center[0], sh.center[1], sh.radius, 0.0, v.real, v.imag])
+        else:
+            raise TypeError("rasterize handles Box and Cylinder")
+    arr = np.ascontiguousarray(np.array(rows, dtype=np.float64).reshape(-1, 7))
+    gc = g.as_c()
+    check(lib().fdfd_rasterize(ctx.handle, C.byref(gc), len(rows), ptr(arr) if len(rows) else None, ptr(eps)), ctx.handle)
+    return eps
+
+
 class Problem:
     """Resident problem: eps_r, coefficients and the multigrid hierarchy stay in HBM between solves."""
 
@@ -465,6 +484,14 @@ class Problem:
         ms = C.c_double()
         check(lib().fdfd_problem_bench_apply(self._h, nrep, C.byref(ms)), self.ctx.handle)
         return ms.value
+
+    def flux_x(self, center, width, forward_h=False):
+        """flux_surface_integral(field, center, width, x̂) (src/flux.jl:37-47) evaluated on the device from the resident Ez"""
+        center = _pt(center)
+        out = C.c_double()
+        w = 1e300 if np.isinf(width) else float(width)
+        check(lib().fdfd_problem_flux_x(self._h, center.x, center.y, w, int(forward_h), C.byref(out)), self.ctx.handle)
+        return out.value
 
     def history(self, nmax=100000):
         """relative (recurrence) residual per iteration of the last solve"""

@@ -62,6 +62,7 @@ EXPORTS = [
     "fdfd_problem_create", "fdfd_problem_destroy", "fdfd_problem_set_rhs", "fdfd_problem_set_source",
     "fdfd_problem_solve", "fdfd_problem_get_solution", "fdfd_problem_get_fields", "fdfd_problem_bench_apply",
     "fdfd_problem_precond", "fdfd_problem_get_history", "fdfd_debug_hess_eig",
+    "fdfd_problem_flux_x", "fdfd_rasterize",
 ]
 
 
@@ -103,6 +104,8 @@ def lib():
         L.fdfd_problem_precond.argtypes = [vp, vp, vp]
         L.fdfd_problem_get_history.argtypes = [vp, vp, i32, C.POINTER(i32)]
         L.fdfd_debug_hess_eig.argtypes = [i32, vp, vp, vp]
+        L.fdfd_problem_flux_x.argtypes = [vp, dbl, dbl, dbl, i32, C.POINTER(dbl)]
+        L.fdfd_rasterize.argtypes = [vp, G, i32, vp, vp]
         _lib = L
     return _lib
 

@@ -1,6 +1,7 @@
 // mg.cu -- shifted-Laplacian geometric multigrid (see mg.cuh for the design).
 #include "mg.cuh"
 #include <cmath>
+#include <string>
 
 namespace {
 
@@ -440,6 +441,136 @@ k_restrict_tile(OpView<T> op, const cplx<T>* __restrict__ u, const cplx<T>* __re
   fc[I + nxc * J] = acc;
 }
 
+// ---- register-marching variants (fewest instructions per point) ------------------------------------------------
+// One thread per fine column marches down the rows keeping the three y-neighbours of the (corrected) iterate in
+// registers; x-neighbours come from warp shuffles, so lanes 0 and 31 of each warp are halo lanes (30 useful columns
+// per warp).  Per point: one interpolation, one u / f / mass load, one store -- the shared-memory tile versions spent
+// ~130 instructions per point (issue bound at 3.2 TB/s).
+constexpr int kMW = 30, kMWarps = 4, kMRows = 32;
+
+template <typename T> __device__ __forceinline__ cplx<T> shfl_up_c(cplx<T> v) {
+  return cplx<T>(__shfl_up_sync(0xffffffffu, v.x, 1), __shfl_up_sync(0xffffffffu, v.y, 1));
+}
+template <typename T> __device__ __forceinline__ cplx<T> shfl_dn_c(cplx<T> v) {
+  return cplx<T>(__shfl_down_sync(0xffffffffu, v.x, 1), __shfl_down_sync(0xffffffffu, v.y, 1));
+}
+
+template <typename T, bool TE, bool PROLONG>
+__global__ void __launch_bounds__(32 * kMWarps)
+k_smooth2_march(OpView<T> op, const cplx<T>* __restrict__ u, const cplx<T>* __restrict__ f, cplx<T>* __restrict__ out,
+                cplx<T>* __restrict__ rxs, cplx<T>* __restrict__ rys, int npx, int npy, T wj, ProlongView<T> pv,
+                const int* __restrict__ done) {
+  if (done && *done) return;
+  const int nx = (int)op.nx, ny = (int)op.ny;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col0 = (blockIdx.x * kMWarps + warp) * kMW;
+  if (col0 >= nx) return;                      // whole warp idle (no block-level barriers in this kernel)
+  const int ix = col0 + lane - 1;              // lanes 0 / 31: left / right halo column
+  const bool valid = ix <= nx;                 // ix == -1 and ix == nx are periodic halos
+  const bool useful = lane >= 1 && lane <= kMW && ix < nx;
+  const int ixw = !valid ? 0 : (ix < 0 ? nx - 1 : (ix == nx ? 0 : ix));
+  const int y0 = blockIdx.y * kMRows;
+  const cplx<T> zero(T(0), T(0));
+  cplx<T> cW = zero, cE = zero;
+  bool xs = false;
+  int ixp = 0;
+  if (useful) { cW = op.cxm[ix]; cE = op.cxp[ix]; xs = in_strip(ix, nx, npx); ixp = ix + 1 == nx ? 0 : ix + 1; }
+  const int iym0 = y0 == 0 ? ny - 1 : y0 - 1;
+  cplx<T> vS = valid ? iterate32<T, PROLONG>(u, pv, nx, ny, ixw, iym0) : zero;
+  cplx<T> vC = valid ? iterate32<T, PROLONG>(u, pv, nx, ny, ixw, y0) : zero;
+  for (int r = 0; r < kMRows; ++r) {
+    const int iy = y0 + r;
+    if (iy >= ny) break;                       // uniform over the CTA
+    const int iyp = iy + 1 == ny ? 0 : iy + 1;
+    const cplx<T> vN = valid ? iterate32<T, PROLONG>(u, pv, nx, ny, ixw, iyp) : zero;
+    const cplx<T> vW = shfl_up_c(vC), vE = shfl_dn_c(vC);
+    if (useful) {
+      const int n = ix + nx * iy;
+      const bool ys = in_strip(iy, ny, npy);
+      cplx<T> W = cW, E = cE, S = op.cym[iy], Nn = op.cyp[iy], m;
+      if (TE) {
+        W = W * op.gx[n]; E = E * op.gx[ixp + nx * iy]; S = S * op.gy[n]; Nn = Nn * op.gy[ix + nx * iyp];
+        m = op.mass_const;
+      } else m = op.mass[n];
+      const cplx<T> C = m - W - E - S - Nn;
+      cplx<T> res = f[n];
+      res -= C * vC; res -= W * vW; res -= E * vE; res -= S * vS; res -= Nn * vN;
+      if (xs) rxs[(int)strip_line(ix, nx, npx) * ny + iy] = res;
+      if (ys) rys[(int)strip_line(iy, ny, npy) * nx + ix] = res;
+      out[n] = (xs || ys) ? vC : vC + wj * cdiv(res, C);
+    }
+    vS = vC; vC = vN;
+  }
+}
+
+// residual + restriction, marching: lanes 1..30 hold residual columns, even-ix lanes 2..28 own coarse points; the
+// x-part of the (separable) restriction comes from shuffles of the residual, the y-part accumulates in registers over
+// the three fine rows of a coarse row.  fine column of lane l: c0 + l - 2, c0 = 28 * warp index (even).
+constexpr int kRWc = 28, kRCRows = 16;   // fine columns with a coarse owner per warp; coarse rows per CTA
+
+template <typename T, bool TE>
+__global__ void __launch_bounds__(32 * kMWarps)
+k_restrict_march(OpView<T> op, const cplx<T>* __restrict__ u, const cplx<T>* __restrict__ f, int64_t nxc64, int64_t nyc64,
+                 const cplx<T>* __restrict__ rx, const cplx<T>* __restrict__ ry, cplx<T>* __restrict__ fc,
+                 const int* __restrict__ done) {
+  if (done && *done) return;
+  const int nx = (int)op.nx, ny = (int)op.ny, nxc = (int)nxc64, nyc = (int)nyc64;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = (blockIdx.x * kMWarps + warp) * kRWc;
+  if (c0 >= nx) return;
+  const int ix = c0 + lane - 2;                                   // in [-2, nx + 1]
+  const bool valid = ix <= nx + 1;
+  const int ixw = !valid ? 0 : wrap32(ix, nx);
+  const bool has_res = lane >= 1 && lane <= 30 && valid;         // residual defined (both x-neighbours in the warp)
+  const bool owner = lane >= 2 && lane <= 28 && (lane & 1) == 0 && ix < nx;  // even ix: coarse point I = ix / 2
+  const int I = ix >> 1;
+  const cplx<T> zero(T(0), T(0));
+  cplx<T> cW = zero, cE = zero, w0 = zero, w1 = zero, w2 = zero;
+  if (has_res) { cW = op.cxm[ixw]; cE = op.cxp[ixw]; }
+  if (owner) { w0 = rx[3 * I]; w1 = rx[3 * I + 1]; w2 = rx[3 * I + 2]; }
+  const int J0 = blockIdx.y * kRCRows;
+  const int ixpw = ixw + 1 == nx ? 0 : ixw + 1;
+  // fine rows 2 J0 - 1 ... 2 (J0 + CR - 1) + 1 ; iterate rows one further on each side
+  int iy = wrap32(2 * J0 - 1, ny);
+  cplx<T> vS = valid ? u[ixw + nx * wrap32(2 * J0 - 2, ny)] : zero;
+  cplx<T> vC = valid ? u[ixw + nx * iy] : zero;
+  cplx<T> acc = zero, acc_next = zero;
+  for (int r = 0; r < 2 * kRCRows + 1; ++r) {
+    const int J = J0 + (r >> 1);                 // r even: fine row 2J - 1 (bottom of J) ; r odd: fine row 2J
+    if (J > nyc || (J == nyc && (r & 1))) break;  // uniform
+    const int iyp = iy + 1 == ny ? 0 : iy + 1;
+    const cplx<T> vN = valid ? u[ixw + nx * iyp] : zero;
+    const cplx<T> vW = shfl_up_c(vC), vE = shfl_dn_c(vC);
+    cplx<T> res = zero;
+    if (has_res) {
+      const int n = ixw + nx * iy;
+      cplx<T> W = cW, E = cE, S = op.cym[iy], Nn = op.cyp[iy], m;
+      if (TE) {
+        W = W * op.gx[n]; E = E * op.gx[ixpw + nx * iy]; S = S * op.gy[n]; Nn = Nn * op.gy[ixw + nx * iyp];
+        m = op.mass_const;
+      } else m = op.mass[n];
+      const cplx<T> C = m - W - E - S - Nn;
+      res = f[n];
+      res -= C * vC; res -= W * vW; res -= E * vE; res -= S * vS; res -= Nn * vN;
+    }
+    const cplx<T> rl = shfl_up_c(res), rr = shfl_dn_c(res);
+    if (owner) {
+      const cplx<T> rxrow = w0 * rl + w1 * res + w2 * rr;
+      if ((r & 1) == 0) {                        // fine row 2J - 1: top of coarse J-1 (already added below), bottom of J
+        if (J < nyc) acc_next = ry[3 * J] * rxrow;
+        if (r > 0) {                             // completes coarse row J - 1
+          acc += ry[3 * (J - 1) + 2] * rxrow;
+          fc[I + nxc * (J - 1)] = acc;
+        }
+        acc = acc_next;
+      } else {                                   // fine row 2J: centre of coarse J
+        acc += ry[3 * J + 1] * rxrow;
+      }
+    }
+    vS = vC; vC = vN; iy = iyp;
+  }
+}
+
 template <typename T>
 __global__ void k_lines2(int64_t nx, int64_t ny, int npx, int npy, int Ky, int Kx, const cplx<T>* __restrict__ mult_y,
                          const cplx<T>* __restrict__ mult_x, const cplx<T>* __restrict__ rxs, const cplx<T>* __restrict__ rys,
@@ -829,9 +960,12 @@ template <typename T> int Multigrid<T>::smooth(int l, bool zero, bool prolong) {
   cplx<T>* out = zero ? L.u.p : L.tmp.p;
   ProlongView<T> pv{0, 0, nullptr, nullptr, nullptr};
   if (prolong) { MGLevel<T>& C = lv[l + 1]; pv = ProlongView<T>{C.nx, C.ny, L.pw.p, L.pw.p + 2 * L.nx, C.u.p}; }
+  static const bool use_tile = []() { const char* e = getenv("FDFD_MG_KERNELS"); return e && std::string(e) == "tile"; }();
   dim3 tgrid((unsigned)((L.nx + kTX - 1) / kTX), (unsigned)((L.ny + kTY - 1) / kTY));
+  dim3 mgrid((unsigned)((L.nx + kMW * kMWarps - 1) / (kMW * kMWarps)), (unsigned)((L.ny + kMRows - 1) / kMRows));
 #define SM2(TEV, ZV, PV) k_smooth2<T, TEV, ZV, PV><<<grid, kMgThreads, 0, ctx->stream>>>(op, L.u.p, L.f.p, out, L.rxs.p, L.rys.p, L.npx, L.npy, wj, pv, done)
-#define SMT(TEV, PV) k_smooth2_tile<T, TEV, PV><<<tgrid, kTileThreads, 0, ctx->stream>>>(op, L.u.p, L.f.p, out, L.rxs.p, L.rys.p, L.npx, L.npy, wj, pv, done)
+#define SMT(TEV, PV) do { if (use_tile) k_smooth2_tile<T, TEV, PV><<<tgrid, kTileThreads, 0, ctx->stream>>>(op, L.u.p, L.f.p, out, L.rxs.p, L.rys.p, L.npx, L.npy, wj, pv, done); \
+    else k_smooth2_march<T, TEV, PV><<<mgrid, 32 * kMWarps, 0, ctx->stream>>>(op, L.u.p, L.f.p, out, L.rxs.p, L.rys.p, L.npx, L.npy, wj, pv, done); } while (0)
   if (te) { if (zero) SM2(true, true, false); else if (prolong) SMT(true, true); else SMT(true, false); }
   else    { if (zero) SM2(false, true, false); else if (prolong) SMT(false, true); else SMT(false, false); }
 #undef SM2
@@ -862,9 +996,16 @@ template <typename T> int Multigrid<T>::cycle(int l, bool zero, int kind) {
   for (int s = 0; s < std::max(1, prm.nu1); ++s) FDFD_TRY(smooth(l, zero && s == 0));
   MGLevel<T>& C = lv[l + 1];
   {
-    dim3 grid((unsigned)((C.nx + kCX - 1) / kCX), (unsigned)((C.ny + kCY - 1) / kCY));
-    if (te) k_restrict_tile<T, true><<<grid, kTileThreads, 0, ctx->stream>>>(L.view(), L.u.p, L.f.p, C.nx, C.ny, L.rw.p, L.rw.p + 3 * C.nx, C.f.p, done);
-    else k_restrict_tile<T, false><<<grid, kTileThreads, 0, ctx->stream>>>(L.view(), L.u.p, L.f.p, C.nx, C.ny, L.rw.p, L.rw.p + 3 * C.nx, C.f.p, done);
+    static const bool use_tile = []() { const char* e = getenv("FDFD_MG_KERNELS"); return e && std::string(e) == "tile"; }();
+    if (use_tile) {
+      dim3 grid((unsigned)((C.nx + kCX - 1) / kCX), (unsigned)((C.ny + kCY - 1) / kCY));
+      if (te) k_restrict_tile<T, true><<<grid, kTileThreads, 0, ctx->stream>>>(L.view(), L.u.p, L.f.p, C.nx, C.ny, L.rw.p, L.rw.p + 3 * C.nx, C.f.p, done);
+      else k_restrict_tile<T, false><<<grid, kTileThreads, 0, ctx->stream>>>(L.view(), L.u.p, L.f.p, C.nx, C.ny, L.rw.p, L.rw.p + 3 * C.nx, C.f.p, done);
+    } else {
+      dim3 grid((unsigned)((L.nx + kRWc * kMWarps - 1) / (kRWc * kMWarps)), (unsigned)((C.ny + kRCRows - 1) / kRCRows));
+      if (te) k_restrict_march<T, true><<<grid, 32 * kMWarps, 0, ctx->stream>>>(L.view(), L.u.p, L.f.p, C.nx, C.ny, L.rw.p, L.rw.p + 3 * C.nx, C.f.p, done);
+      else k_restrict_march<T, false><<<grid, 32 * kMWarps, 0, ctx->stream>>>(L.view(), L.u.p, L.f.p, C.nx, C.ny, L.rw.p, L.rw.p + 3 * C.nx, C.f.p, done);
+    }
     KLAUNCH(ctx);
   }
   if (kind == 2 && l < prm.wdepth) {

@@ -183,6 +183,16 @@ int fdfd_problem_get_history(fdfd_problem* p, double* out, int n, int* written);
 /* one application of the preconditioner M^-1 to a resident vector (parity/debug hook) */
 int fdfd_problem_precond(fdfd_problem* p, const fdfd_c128* in, fdfd_c128* out);
 
+/* ---- callers either side of the path, kept on the device for large sweeps -------------------------
+ * flux_surface_integral(field, Point(center_x, center_y), width, x̂) of the TM solution resident in `p`
+ * (src/flux.jl:37-47); forward_h selects the H recovery of modulation.jl:112-113 / eigen.jl:90-91 instead of
+ * driven.jl:40-41.  One double comes back instead of the (Nx,Ny,3) field. */
+int fdfd_problem_flux_x(fdfd_problem* p, double center_x, double center_y, double width, int forward_h, double* flux);
+/* setup_ϵᵣ!(d, shapes) (src/device.jl:47-61) for boxes/cylinders: shapes7 = nshapes x {kind(0 box,1 cylinder), cx, cy,
+ * a, b, eps_re, eps_im} (box: a,b full widths; cylinder: a radius); the first shape containing a pixel centre wins,
+ * other pixels keep the value already in eps_r (host or device buffer, (Nx,Ny)). */
+int fdfd_rasterize(fdfd_ctx* ctx, const fdfd_grid_t* g, int nshapes, const double* shapes7, fdfd_c128* eps_r);
+
 /* host-only test hook (no GPU needed): the small dense complex Hessenberg eigen-solver behind the Ritz pairs of
  * fdfd_eigenfrequency.  H, evecs: column-major n x n; evals: n. */
 int fdfd_debug_hess_eig(int n, const fdfd_c128* H, fdfd_c128* evals, fdfd_c128* evecs);

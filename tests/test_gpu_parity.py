@@ -269,3 +269,40 @@ def test_graft_entry_smoke():
     """the driver's smoke(): one small solve on cuda:0 checked against the oracle"""
     import __graft_entry__ as ge
     ge.smoke()
+
+
+def test_device_flux_consumer(fdfd):
+    """on-device flux_surface_integral (flux.jl:37-47) == the host consumer on the returned field == oracle"""
+    gargs = (0.02, [15, 10], [0.0, 6.0], [-1.0, 1.0])
+    g, go = fdfd.Grid(*gargs), O.Grid2D(*gargs)
+    d = fdfd.Device(g, W200)
+    fdfd.setup_eps_r(d, [fdfd.Box((3.0, 0.0), (np.inf, 0.3), 12)])
+    fdfd.add_mode(d, fdfd.Mode(fdfd.TM, fdfd.XHAT, 3.5, fdfd.Point(1.0, 0), 0.8))
+    fdfd._apply_modes(d, W200)
+    P = fdfd.Problem(g, fdfd.TM, W200, d.eps_r)
+    P.set_source(d.src)
+    info = P.solve()
+    assert info["flag"] == 0
+    field = fdfd.FieldTM(g, W200, P.fields())
+    for c, w in ((fdfd.Point(3.0, 0.0), np.inf), (fdfd.Point(4.5, 0.1), 0.4)):
+        dev = P.flux_x(c, w)
+        host = fdfd.flux_surface_integral(field, c, w, fdfd.XHAT)
+        assert abs(dev / host - 1) < 1e-10
+    do = O.Device(go, [W200]); do.eps_r[:] = d.eps_r; do.src[:] = d.src
+    fo = O.solve(do, O.TM)
+    assert abs(P.flux_x(fdfd.Point(3.0, 0.0), np.inf) / O.flux_surface_integral_tm_x(go, fo["data"], (3.0, 0), np.inf) - 1) < 1e-6
+    P.close()
+
+
+def test_gpu_rasterizer(fdfd):
+    """setup_ϵᵣ!(d, shapes) on the GPU == the host rasteriser == the oracle's, bit-exact (first containing shape wins)"""
+    g, go = fdfd.Grid(0.01, [15, 15], [-2.0, 2.0], [-2.0, 2.0]), O.Grid2D(0.01, [15, 15], [-2.0, 2.0], [-2.0, 2.0])
+    shapes = [fdfd.Cylinder((0, 0), 0.8, 1.0), fdfd.Cylinder((0, 0), 1.0, 12.25), fdfd.Box((1.2, -0.5), (1.0, np.inf), 2.0 + 0.1j)]
+    got = fdfd.rasterize(g, shapes)
+    d = fdfd.Device(g, W200)
+    fdfd.setup_eps_r(d, shapes)
+    assert np.array_equal(got, d.eps_r)
+    ref = np.ones(go.size(), dtype=complex)
+    O.compose_shapes(ref, go, [(O.cylinder_region((0, 0), 0.8), 1.0), (O.cylinder_region((0, 0), 1.0), 12.25),
+                               (O.box_region((1.2, -0.5), (1.0, np.inf)), 2.0 + 0.1j)])
+    assert np.array_equal(got, ref)
