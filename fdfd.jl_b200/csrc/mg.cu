@@ -406,26 +406,51 @@ k_restrict_tile(OpView<T> op, const cplx<T>* __restrict__ u, const cplx<T>* __re
     sgy[threadIdx.x - 128] = gy; scym[threadIdx.x - 128] = op.cym[gy]; scyp[threadIdx.x - 128] = op.cyp[gy];
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < kUW * kUH; idx += kTileThreads) {  // 1-D: every pass is full width
-    const int lx = idx % kUW, ly = idx / kUW;
-    su[idx] = u[sgx[lx] + nx * sgy[ly]];
+  {
+    constexpr int NU = (kUW * kUH + kTileThreads - 1) / kTileThreads;
+    cplx<T> reg[NU];
+#pragma unroll
+    for (int k = 0; k < NU; ++k) {   // all loads first (memory-level parallelism), then the shared-memory stores
+      const int idx = min(threadIdx.x + k * kTileThreads, kUW * kUH - 1);
+      const int lx = idx % kUW, ly = idx / kUW;
+      reg[k] = u[sgx[lx] + nx * sgy[ly]];
+    }
+#pragma unroll
+    for (int k = 0; k < NU; ++k) {
+      const int idx = threadIdx.x + k * kTileThreads;
+      if (idx < kUW * kUH) su[idx] = reg[k];
+    }
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < kRW * kRH; idx += kTileThreads) {
-    const int lx = idx % kRW, ly = idx / kRW;
-    const int ix = sgx[lx + 1], iy = sgy[ly + 1];
-    const int n = ix + nx * iy;
-    cplx<T> W = scxm[lx + 1], E = scxp[lx + 1], S = scym[ly + 1], Nn = scyp[ly + 1], m;
-    if (TE) {
-      const int ixp = ix + 1 == nx ? 0 : ix + 1, iyp = iy + 1 == ny ? 0 : iy + 1;
-      W = W * op.gx[n]; E = E * op.gx[ixp + nx * iy]; S = S * op.gy[n]; Nn = Nn * op.gy[ix + nx * iyp];
-      m = op.mass_const;
-    } else m = op.mass[n];
-    const cplx<T> C = m - W - E - S - Nn;
-    const cplx<T>* t = su + (ly + 1) * kUW + (lx + 1);
-    cplx<T> res = f[n];
-    res -= C * t[0]; res -= W * t[-1]; res -= E * t[1]; res -= S * t[-kUW]; res -= Nn * t[kUW];
-    sr[idx] = res;
+  {
+    constexpr int NR = (kRW * kRH + kTileThreads - 1) / kTileThreads;
+    cplx<T> fv[NR], mv[NR];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+      const int idx = min(threadIdx.x + k * kTileThreads, kRW * kRH - 1);
+      const int lx = idx % kRW, ly = idx / kRW;
+      const int n = sgx[lx + 1] + nx * sgy[ly + 1];
+      fv[k] = f[n];
+      mv[k] = TE ? op.mass_const : op.mass[n];
+    }
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+      const int idx = threadIdx.x + k * kTileThreads;
+      if (idx >= kRW * kRH) break;
+      const int lx = idx % kRW, ly = idx / kRW;
+      cplx<T> W = scxm[lx + 1], E = scxp[lx + 1], S = scym[ly + 1], Nn = scyp[ly + 1];
+      if (TE) {
+        const int ix = sgx[lx + 1], iy = sgy[ly + 1];
+        const int n = ix + nx * iy;
+        const int ixp = ix + 1 == nx ? 0 : ix + 1, iyp = iy + 1 == ny ? 0 : iy + 1;
+        W = W * op.gx[n]; E = E * op.gx[ixp + nx * iy]; S = S * op.gy[n]; Nn = Nn * op.gy[ix + nx * iyp];
+      }
+      const cplx<T> C = mv[k] - W - E - S - Nn;
+      const cplx<T>* t = su + (ly + 1) * kUW + (lx + 1);
+      cplx<T> res = fv[k];
+      res -= C * t[0]; res -= W * t[-1]; res -= E * t[1]; res -= S * t[-kUW]; res -= Nn * t[kUW];
+      sr[idx] = res;
+    }
   }
   __syncthreads();
   const int ci = threadIdx.x % kCX, cj = threadIdx.x / kCX;
@@ -960,7 +985,7 @@ template <typename T> int Multigrid<T>::smooth(int l, bool zero, bool prolong) {
   cplx<T>* out = zero ? L.u.p : L.tmp.p;
   ProlongView<T> pv{0, 0, nullptr, nullptr, nullptr};
   if (prolong) { MGLevel<T>& C = lv[l + 1]; pv = ProlongView<T>{C.nx, C.ny, L.pw.p, L.pw.p + 2 * L.nx, C.u.p}; }
-  static const bool use_tile = []() { const char* e = getenv("FDFD_MG_KERNELS"); return e && std::string(e) == "tile"; }();
+  static const bool use_tile = []() { const char* e = getenv("FDFD_MG_KERNELS"); return !(e && std::string(e) == "march"); }();
   dim3 tgrid((unsigned)((L.nx + kTX - 1) / kTX), (unsigned)((L.ny + kTY - 1) / kTY));
   dim3 mgrid((unsigned)((L.nx + kMW * kMWarps - 1) / (kMW * kMWarps)), (unsigned)((L.ny + kMRows - 1) / kMRows));
 #define SM2(TEV, ZV, PV) k_smooth2<T, TEV, ZV, PV><<<grid, kMgThreads, 0, ctx->stream>>>(op, L.u.p, L.f.p, out, L.rxs.p, L.rys.p, L.npx, L.npy, wj, pv, done)
@@ -996,7 +1021,7 @@ template <typename T> int Multigrid<T>::cycle(int l, bool zero, int kind) {
   for (int s = 0; s < std::max(1, prm.nu1); ++s) FDFD_TRY(smooth(l, zero && s == 0));
   MGLevel<T>& C = lv[l + 1];
   {
-    static const bool use_tile = []() { const char* e = getenv("FDFD_MG_KERNELS"); return e && std::string(e) == "tile"; }();
+    static const bool use_tile = []() { const char* e = getenv("FDFD_MG_KERNELS"); return !(e && std::string(e) == "march"); }();
     if (use_tile) {
       dim3 grid((unsigned)((C.nx + kCX - 1) / kCX), (unsigned)((C.ny + kCY - 1) / kCY));
       if (te) k_restrict_tile<T, true><<<grid, kTileThreads, 0, ctx->stream>>>(L.view(), L.u.p, L.f.p, C.nx, C.ny, L.rw.p, L.rw.p + 3 * C.nx, C.f.p, done);
