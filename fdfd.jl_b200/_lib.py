@@ -63,7 +63,11 @@ EXPORTS = [
     "fdfd_problem_solve", "fdfd_problem_get_solution", "fdfd_problem_get_fields", "fdfd_problem_bench_apply",
     "fdfd_problem_precond", "fdfd_problem_get_history", "fdfd_debug_hess_eig",
     "fdfd_problem_flux_x", "fdfd_rasterize",
+    "fdfd_comm_unique_id", "fdfd_comm_create_nccl", "fdfd_comm_group_create", "fdfd_comm_group_destroy",
+    "fdfd_comm_create_threads", "fdfd_comm_destroy", "fdfd_slab_rows", "fdfd_solve_driven_slab", "fdfd_comm_stats",
 ]
+COMM_THREADS, COMM_NCCL = 0, 1
+COMM_ID_BYTES = 128
 
 
 def lib():
@@ -106,6 +110,17 @@ def lib():
         L.fdfd_debug_hess_eig.argtypes = [i32, vp, vp, vp]
         L.fdfd_problem_flux_x.argtypes = [vp, dbl, dbl, dbl, i32, C.POINTER(dbl)]
         L.fdfd_rasterize.argtypes = [vp, G, i32, vp, vp]
+        L.fdfd_comm_unique_id.argtypes = [vp]
+        L.fdfd_comm_create_nccl.argtypes = [vp, i32, i32, vp, C.POINTER(vp)]
+        L.fdfd_comm_group_create.argtypes = [i32, C.POINTER(vp)]
+        L.fdfd_comm_group_destroy.argtypes = [vp]
+        L.fdfd_comm_group_destroy.restype = None
+        L.fdfd_comm_create_threads.argtypes = [vp, i32, C.POINTER(vp)]
+        L.fdfd_comm_destroy.argtypes = [vp]
+        L.fdfd_comm_destroy.restype = None
+        L.fdfd_slab_rows.argtypes = [G, i32, i32, C.POINTER(i64), C.POINTER(i64)]
+        L.fdfd_solve_driven_slab.argtypes = [vp, vp, G, dbl, vp, vp, C.POINTER(SolveOpts), vp, C.POINTER(Info)]
+        L.fdfd_comm_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
         _lib = L
     return _lib
 

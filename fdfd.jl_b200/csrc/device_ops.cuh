@@ -15,8 +15,19 @@ template <typename T> struct OpView {
 };
 
 // fp64 fine-grid operator resident in HBM
+// a y-slab of a global grid: owned global rows [y0, y0+nyl), stored with H halo rows on each side
+struct SlabInfo {
+  bool on = false;
+  fdfd_grid_t gg{};        // the global grid
+  int64_t y0 = 0, nyl = 0; // owned rows (fine level)
+  int64_t H = 0;           // fine-level halo width = 2^(nlevels-1)
+  int nlevels = 0;         // multigrid depth, decided on the global grid
+  int64_t yoff() const { return y0 - H; }  // global row of local row 0
+};
+
 struct FineOp {
-  fdfd_grid_t g{};
+  fdfd_grid_t g{};         // grid the arrays are sized for (slab: Nx x (nyl + 2H), same cell size as the global grid)
+  SlabInfo slab;
   int pol = FDFD_TM, ordering = FDFD_ORDER_FB;
   double omega = 0;      // frequency of the mass term
   double omega_pml = 0;  // frequency the PML s-factors are evaluated at (== omega except modulation.jl:79 sharedpml)
@@ -29,6 +40,9 @@ struct FineOp {
 
   int build(fdfd_ctx* ctx, const fdfd_grid_t& g, int pol, int ordering, double omega, const fdfd_c128* eps_r_any,
             double omega_pml = 0.0);
+  // slab of the global grid gg: eps_local_any holds the (nyl + 2H) x Nx local rows (halo rows included, periodic wrap)
+  int build_slab(fdfd_ctx* ctx, const fdfd_grid_t& gg, int ordering, double omega, const fdfd_c128* eps_local_any,
+                 int64_t y0, int64_t nyl, int nlevels);
   OpView<double> view() const {
     OpView<double> v;
     v.nx = g.Nx; v.ny = g.Ny;
@@ -43,7 +57,10 @@ struct FineOp {
 //   ndot = 0: none;  1: partial[0] = <d0, y>;  2: partial[0] = <y, d0>, partial[1] = <y, y>   (conjugate-linear in 1st arg)
 // sideband coupling of the modulated operator (modulation.jl:95-101): y += hw * (conj(deps) x_{j+1} + deps x_{j-1})
 struct Coupling { const void* xm1 = nullptr; const void* xp1 = nullptr; const c128* deps = nullptr; double hw = 0.0; };
-struct DotSpec { int ndot = 0; const c128* d0 = nullptr; c128* partials = nullptr; int* nblocks_out = nullptr; const int* done = nullptr; };
+struct DotSpec {
+  int ndot = 0; const c128* d0 = nullptr; c128* partials = nullptr; int* nblocks_out = nullptr; const int* done = nullptr;
+  int64_t row_lo = 0, row_hi = -1;  // slab mode: rows outside [row_lo,row_hi) are written as 0 and excluded from the dots
+};
 int launch_apply(fdfd_ctx* ctx, const OpView<double>& op, bool te, const void* x, bool x_is_f32, c128* y, const DotSpec& ds,
                  const Coupling* cpl = nullptr);
 

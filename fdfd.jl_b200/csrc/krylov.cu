@@ -101,6 +101,14 @@ k_xr_update(int64_t N, const KScal* __restrict__ sc, c128* __restrict__ x, const
   block_reduce_store<kVecThreads, 4>(acc, reinterpret_cast<double*>(partials) + (size_t)blockIdx.x * 4);
 }
 
+// slab mode: local partials -> 4 doubles (then summed over the ranks by an allreduce) ; K doubles per partial entry
+template <int K>
+__global__ void k_reduce_partials(const c128* __restrict__ partials, int nb, double* __restrict__ lsum) {
+  double res[K];
+  final_reduce<kScalThreads, K>(reinterpret_cast<const double*>(partials), nb, res);
+  if (threadIdx.x == 0) { for (int k = 0; k < 4; ++k) lsum[k] = k < K ? res[k] : 0.0; }
+}
+
 __device__ __forceinline__ bool finite2(c128 a) { return isfinite(a.x) && isfinite(a.y); }
 
 // alpha = rho / <rhat, v>
@@ -184,6 +192,7 @@ int KrylovWork::alloc(fdfd_ctx* ctx, int64_t n_, int nparts, int maxit, bool jac
   if (jacobi_bufs) { WALLOC(ph, n); WALLOC(sh, n); }
   WALLOC(partials, (size_t)nparts * 2);
   WALLOC(scal, 1);
+  WALLOC(lsum, 4);
   WALLOC(hist, (size_t)std::max(16, maxit + 2));
 #undef WALLOC
   if (cudaMallocHost((void**)&h_scal, sizeof(KScal)) != cudaSuccess) { fdfd_set_error(ctx, "cudaMallocHost failed"); return FDFD_ERR_ALLOC; }
@@ -219,8 +228,22 @@ static int bicgstab_loop(fdfd_ctx* ctx, KrylovWork& W, const KrylovOps& ops, con
   const double fscale = ops.fscale;
   const bool use_graph = o.use_graph && st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
 
+  // where the scalar kernels read their sums: the per-CTA partials, or (slab mode) the 4 doubles left by a local reduce
+  // followed by the allreduce over the ranks
+  const c128* sp = W.partials.p; int snb = 0;
+  auto sums = [&](int nb, int K) -> int {
+    sp = W.partials.p; snb = nb;
+    if (!ops.allreduce) return FDFD_OK;
+    if (K == 2) k_reduce_partials<2><<<1, kScalThreads, 0, st>>>(W.partials.p, nb, W.lsum.p);
+    else k_reduce_partials<4><<<1, kScalThreads, 0, st>>>(W.partials.p, nb, W.lsum.p);
+    KLAUNCH(ctx);
+    FDFD_TRY(ops.allreduce(W.lsum.p));
+    sp = reinterpret_cast<const c128*>(W.lsum.p); snb = 1;
+    return FDFD_OK;
+  };
   k_init<<<nvb, kVecThreads, 0, st>>>(N, W.b.p, W.x.p, W.r.p, W.rhat.p, W.p.p, W.v.p, W.partials.p); KLAUNCH(ctx);
-  k_scal_init<<<1, kScalThreads, 0, st>>>(W.partials.p, nvb, sc, o.tol, 0); KLAUNCH(ctx);
+  FDFD_TRY(sums(nvb, 4));
+  k_scal_init<<<1, kScalThreads, 0, st>>>(sp, snb, sc, o.tol, 0); KLAUNCH(ctx);
   CUDA_TRY(ctx, cudaGetLastError());
 
   int restarts = 0, flag = FDFD_OK;
@@ -238,14 +261,17 @@ static int bicgstab_loop(fdfd_ctx* ctx, KrylovWork& W, const KrylovOps& ops, con
         FDFD_TRY(ops.precond(true, &ph));
         DotSpec d1; d1.ndot = 1; d1.d0 = W.rhat.p; d1.partials = W.partials.p; d1.done = &sc->done;
         FDFD_TRY(ops.apply(ph, sizeof(TP) == sizeof(c64), W.v.p, d1));
-        k_scal_alpha<<<1, kScalThreads, 0, st>>>(W.partials.p, nab, sc); KLAUNCH(ctx);
+        FDFD_TRY(sums(nab, 2));
+        k_scal_alpha<<<1, kScalThreads, 0, st>>>(sp, snb, sc); KLAUNCH(ctx);
         k_s_update<TP><<<nvb, kVecThreads, 0, st>>>(N, sc, W.r.p, W.v.p, W.s.p, prhs, fscale); KLAUNCH(ctx);
         FDFD_TRY(ops.precond(false, &sh));
         DotSpec d2; d2.ndot = 2; d2.d0 = W.s.p; d2.partials = W.partials.p; d2.done = &sc->done;
         FDFD_TRY(ops.apply(sh, sizeof(TP) == sizeof(c64), W.t.p, d2));
-        k_scal_omega<<<1, kScalThreads, 0, st>>>(W.partials.p, nab, sc); KLAUNCH(ctx);
+        FDFD_TRY(sums(nab, 4));
+        k_scal_omega<<<1, kScalThreads, 0, st>>>(sp, snb, sc); KLAUNCH(ctx);
         k_xr_update<TP><<<nvb, kVecThreads, 0, st>>>(N, sc, W.x.p, (const TP*)ph, (const TP*)sh, W.s.p, W.t.p, W.r.p, W.rhat.p, W.partials.p); KLAUNCH(ctx);
-        k_scal_rho<<<1, kScalThreads, 0, st>>>(W.partials.p, nvb, sc, W.hist.p, hist_len); KLAUNCH(ctx);
+        FDFD_TRY(sums(nvb, 4));
+        k_scal_rho<<<1, kScalThreads, 0, st>>>(sp, snb, sc, W.hist.p, hist_len); KLAUNCH(ctx);
         return FDFD_OK;
       };
       if (!use_graph) { FDFD_TRY(one_iteration()); continue; }
@@ -287,7 +313,8 @@ static int bicgstab_loop(fdfd_ctx* ctx, KrylovWork& W, const KrylovOps& ops, con
     DotSpec d0;
     FDFD_TRY(ops.apply(W.x.p, false, W.t.p, d0));
     k_true_resid<<<nvb, kVecThreads, 0, st>>>(N, W.b.p, W.t.p, W.partials.p); KLAUNCH(ctx);
-    k_scal_init<<<1, kScalThreads, 0, st>>>(W.partials.p, nvb, sc, o.tol, 2); KLAUNCH(ctx);
+    FDFD_TRY(sums(nvb, 4));
+    k_scal_init<<<1, kScalThreads, 0, st>>>(sp, snb, sc, o.tol, 2); KLAUNCH(ctx);
     CUDA_TRY(ctx, cudaMemcpyAsync(W.h_scal, sc, sizeof(KScal), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     true_rel = std::sqrt(W.h_scal->rr / W.h_scal->bnorm2);
@@ -299,7 +326,8 @@ static int bicgstab_loop(fdfd_ctx* ctx, KrylovWork& W, const KrylovOps& ops, con
     // ---- restart from the current x (cures breakdown and recurrence drift)
     ++restarts;
     k_restart<<<nvb, kVecThreads, 0, st>>>(N, W.b.p, W.t.p, W.r.p, W.rhat.p, W.p.p, W.v.p, W.partials.p); KLAUNCH(ctx);
-    k_scal_init<<<1, kScalThreads, 0, st>>>(W.partials.p, nvb, sc, o.tol, 1); KLAUNCH(ctx);
+    FDFD_TRY(sums(nvb, 4));
+    k_scal_init<<<1, kScalThreads, 0, st>>>(sp, snb, sc, o.tol, 1); KLAUNCH(ctx);
   }
   info->iters = W.h_scal->iter;
   info->relres = true_rel;

@@ -23,6 +23,7 @@ struct KrylovWork {
   DevBuf<c128> ph, sh;      // fp64 preconditioned vectors (Jacobi only)
   DevBuf<c128> partials;    // per-CTA partial sums, [block][<=2] complex
   DevBuf<KScal> scal;
+  DevBuf<double> lsum;      // slab mode: locally reduced sums handed to the allreduce
   DevBuf<double> hist;      // ||r||^2 per iteration
   KScal* h_scal = nullptr;  // pinned mirror
   int nvec_blocks = 0;
@@ -41,6 +42,7 @@ struct KrylovOps {
   std::function<int(const void* x, bool x_f32, c128* y, const DotSpec& ds)> apply;
   // result of M^-1 applied to the vector previously written to prec_rhs (or to p / s when prec_rhs == null)
   std::function<int(bool hold, const void** out)> precond;
+  std::function<int(double* dev4)> allreduce;                    // slab mode: sum 4 doubles over the ranks (in place, on the stream)
   std::function<void(std::vector<void*>&)> get_state;            // buffer-rotation state (may be empty)
   std::function<void(const std::vector<void*>&)> set_state;
 };

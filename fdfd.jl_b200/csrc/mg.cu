@@ -45,6 +45,10 @@ __device__ __forceinline__ cplx<T> residual_at(const OpView<T>& op, const cplx<T
 __device__ __forceinline__ bool in_strip(int64_t i, int64_t n, int np) { return i < np || i >= n - np; }
 __device__ __forceinline__ int64_t strip_line(int64_t i, int64_t n, int np) { return i < np ? i : i - (n - 2 * np); }
 __device__ __forceinline__ int64_t strip_index(int64_t c, int64_t n, int np) { return c < np ? c : c + (n - 2 * np); }
+// y-strip rows as two ranges [a0,a1) U [b0,b1) (a slab owns only part of the global PML rows, see slab.cu)
+__device__ __forceinline__ bool ys_in(const YS& s, int iy) { return (iy >= s.a0 && iy < s.a1) || (iy >= s.b0 && iy < s.b1); }
+__device__ __forceinline__ int ys_line(const YS& s, int iy) { return iy < s.a1 ? iy - s.a0 : (s.a1 - s.a0) + (iy - s.b0); }
+__device__ __forceinline__ int ys_row(const YS& s, int c) { const int na = s.a1 - s.a0; return c < na ? s.a0 + c : s.b0 + (c - na); }
 
 // ---- level setup --------------------------------------------------------------------------
 // TM: mass = (1 - i beta) w^2 eps0 eps ;  TE: gx, gy = 1/grid_average(eps0 eps)
@@ -101,11 +105,11 @@ __global__ void k_restrict_eps(int64_t nxf, int64_t nyf, int64_t nxc, int64_t ny
 // mode 0: y-lines (column ix = strip_index(c)), a=S, c=N.  mode 1: x-lines (row iy), a=W, c=E.  Wrap couplings
 // are dropped (they link the two deepest PML cells and stay in the lagged part of the splitting).
 template <typename T, bool TE>
-__global__ void k_pcr_setup(OpView<T> op, int mode, int np, int K, c128* __restrict__ scratch, cplx<T>* __restrict__ mult) {
+__global__ void k_pcr_setup(OpView<T> op, int mode, int np, YS ys, int K, c128* __restrict__ scratch, cplx<T>* __restrict__ mult) {
   const int64_t nx = op.nx, ny = op.ny;
   const int64_t n = mode == 0 ? ny : nx;
   const int64_t c = blockIdx.x;
-  const int64_t fixed = strip_index(c, mode == 0 ? nx : ny, np);
+  const int64_t fixed = mode == 0 ? strip_index(c, nx, np) : (int64_t)ys_row(ys, (int)c);
   c128* a0 = scratch + (size_t)c * 6 * n; c128* b0 = a0 + n; c128* c0 = b0 + n;
   c128* a1 = c0 + n; c128* b1 = a1 + n; c128* c1 = b1 + n;
   cplx<T>* alpha = mult + (size_t)c * (2 * K + 1) * n;
@@ -261,7 +265,7 @@ __device__ __forceinline__ cplx<T> iterate_at(const cplx<T>* __restrict__ u, con
 template <typename T, bool TE, bool ZERO, bool PROLONG>
 __global__ void __launch_bounds__(kMgThreads)
 k_smooth2(OpView<T> op, const cplx<T>* __restrict__ u, const cplx<T>* __restrict__ f, cplx<T>* __restrict__ out,
-          cplx<T>* __restrict__ rxs, cplx<T>* __restrict__ rys, int npx, int npy, T wj, ProlongView<T> pv,
+          cplx<T>* __restrict__ rxs, cplx<T>* __restrict__ rys, int npx, YS ysr, T wj, ProlongView<T> pv,
           const int* __restrict__ done) {
   if (done && *done) return;
   const int64_t nx = op.nx, ny = op.ny;
@@ -274,7 +278,7 @@ k_smooth2(OpView<T> op, const cplx<T>* __restrict__ u, const cplx<T>* __restrict
     const int64_t iy = blockIdx.y * (int64_t)kMgRows + r;
     if (iy >= ny) break;
     const int64_t n = ix + nx * iy;
-    const bool ys = in_strip(iy, ny, npy);
+    const bool ys = ys_in(ysr, (int)iy);
     const int64_t iym = iy == 0 ? ny - 1 : iy - 1, iyp = iy + 1 == ny ? 0 : iy + 1;
     cplx<T> W, E, S, Nn, C;
     row_coefs<T, TE>(op, ix, iy, ixp, iyp, W, E, S, Nn, C);
@@ -288,7 +292,7 @@ k_smooth2(OpView<T> op, const cplx<T>* __restrict__ u, const cplx<T>* __restrict
       res -= Nn * iterate_at<T, PROLONG>(u, pv, nx, ny, ix, iyp);
     }
     if (xs) rxs[strip_line(ix, nx, npx) * ny + iy] = res;
-    if (ys) rys[strip_line(iy, ny, npy) * nx + ix] = res;
+    if (ys) rys[ys_line(ysr, (int)iy) * nx + ix] = res;
     out[n] = (xs || ys) ? u0 : u0 + wj * cdiv(res, C);
   }
 }
@@ -326,7 +330,7 @@ __device__ __forceinline__ cplx<T> iterate32(const cplx<T>* __restrict__ u, cons
 template <typename T, bool TE, bool PROLONG>
 __global__ void __launch_bounds__(kTileThreads)
 k_smooth2_tile(OpView<T> op, const cplx<T>* __restrict__ u, const cplx<T>* __restrict__ f, cplx<T>* __restrict__ out,
-               cplx<T>* __restrict__ rxs, cplx<T>* __restrict__ rys, int npx, int npy, T wj, ProlongView<T> pv,
+               cplx<T>* __restrict__ rxs, cplx<T>* __restrict__ rys, int npx, YS ysr, T wj, ProlongView<T> pv,
                const int* __restrict__ done) {
   if (done && *done) return;
   __shared__ cplx<T> tile[(kTY + 2) * (kTX + 2)];
@@ -353,7 +357,7 @@ k_smooth2_tile(OpView<T> op, const cplx<T>* __restrict__ u, const cplx<T>* __res
     const int iy = y0 + ly;
     if (iy >= ny) break;
     const int n = ix + nx * iy;
-    const bool ys = in_strip(iy, ny, npy);
+    const bool ys = ys_in(ysr, (int)iy);
     cplx<T> W = cW, E = cE, S = op.cym[iy], Nn = op.cyp[iy], m;
     if (TE) {
       const int iyp = iy + 1 == ny ? 0 : iy + 1;
@@ -366,7 +370,7 @@ k_smooth2_tile(OpView<T> op, const cplx<T>* __restrict__ u, const cplx<T>* __res
     cplx<T> res = f[n];
     res -= C * u0; res -= W * t[-1]; res -= E * t[1]; res -= S * t[-(kTX + 2)]; res -= Nn * t[kTX + 2];
     if (xs) rxs[(int)strip_line(ix, nx, npx) * ny + iy] = res;
-    if (ys) rys[(int)strip_line(iy, ny, npy) * nx + ix] = res;
+    if (ys) rys[(int)ys_line(ysr, (int)iy) * nx + ix] = res;
     out[n] = (xs || ys) ? u0 : u0 + wj * cdiv(res, C);
   }
 }
@@ -483,7 +487,7 @@ template <typename T> __device__ __forceinline__ cplx<T> shfl_dn_c(cplx<T> v) {
 template <typename T, bool TE, bool PROLONG>
 __global__ void __launch_bounds__(32 * kMWarps)
 k_smooth2_march(OpView<T> op, const cplx<T>* __restrict__ u, const cplx<T>* __restrict__ f, cplx<T>* __restrict__ out,
-                cplx<T>* __restrict__ rxs, cplx<T>* __restrict__ rys, int npx, int npy, T wj, ProlongView<T> pv,
+                cplx<T>* __restrict__ rxs, cplx<T>* __restrict__ rys, int npx, YS ysr, T wj, ProlongView<T> pv,
                 const int* __restrict__ done) {
   if (done && *done) return;
   const int nx = (int)op.nx, ny = (int)op.ny;
@@ -511,7 +515,7 @@ k_smooth2_march(OpView<T> op, const cplx<T>* __restrict__ u, const cplx<T>* __re
     const cplx<T> vW = shfl_up_c(vC), vE = shfl_dn_c(vC);
     if (useful) {
       const int n = ix + nx * iy;
-      const bool ys = in_strip(iy, ny, npy);
+      const bool ys = ys_in(ysr, (int)iy);
       cplx<T> W = cW, E = cE, S = op.cym[iy], Nn = op.cyp[iy], m;
       if (TE) {
         W = W * op.gx[n]; E = E * op.gx[ixp + nx * iy]; S = S * op.gy[n]; Nn = Nn * op.gy[ix + nx * iyp];
@@ -521,7 +525,7 @@ k_smooth2_march(OpView<T> op, const cplx<T>* __restrict__ u, const cplx<T>* __re
       cplx<T> res = f[n];
       res -= C * vC; res -= W * vW; res -= E * vE; res -= S * vS; res -= Nn * vN;
       if (xs) rxs[(int)strip_line(ix, nx, npx) * ny + iy] = res;
-      if (ys) rys[(int)strip_line(iy, ny, npy) * nx + ix] = res;
+      if (ys) rys[(int)ys_line(ysr, (int)iy) * nx + ix] = res;
       out[n] = (xs || ys) ? vC : vC + wj * cdiv(res, C);
     }
     vS = vC; vC = vN;
@@ -597,7 +601,7 @@ k_restrict_march(OpView<T> op, const cplx<T>* __restrict__ u, const cplx<T>* __r
 }
 
 template <typename T>
-__global__ void k_lines2(int64_t nx, int64_t ny, int npx, int npy, int Ky, int Kx, const cplx<T>* __restrict__ mult_y,
+__global__ void k_lines2(int64_t nx, int64_t ny, int npx, YS ys, int Ky, int Kx, const cplx<T>* __restrict__ mult_y,
                          const cplx<T>* __restrict__ mult_x, const cplx<T>* __restrict__ rxs, const cplx<T>* __restrict__ rys,
                          cplx<T>* __restrict__ out, T wl, cplx<T>* __restrict__ gscratch, const int* __restrict__ done) {
   if (done && *done) return;
@@ -665,10 +669,10 @@ __global__ void k_lines2(int64_t nx, int64_t ny, int npx, int npy, int Ky, int K
       cplx<T>* t = d0; d0 = d1; d1 = t;
     }
   }
-  const int fixed = (int)strip_index(c, ymode ? nx : ny, ymode ? npx : npy);
+  const int fixed = ymode ? (int)strip_index(c, nx, npx) : ys_row(ys, c);
   const int inx = (int)nx;
   for (int i = tid; i < n; i += nt) {
-    if (ymode && in_strip(i, ny, npy)) continue;  // corners belong to the x-lines
+    if (ymode && ys_in(ys, i)) continue;  // corners belong to the x-lines
     const int64_t idx = ymode ? (int64_t)fixed + (int64_t)inx * i : (int64_t)i + (int64_t)inx * fixed;
     out[idx] += wl * (d0[i] * binv[i]);
   }
@@ -777,6 +781,26 @@ static void hier_coefs(const Hier1D& H, int l, double scale_over_h2, std::vector
   for (int64_t i = 0; i < n; ++i) { cm[i] = scale_over_h2 / (V[i] * E[i]); cp[i] = scale_over_h2 / (V[i] * E[(i + 1) % n]); }
 }
 
+// level sizes of the hierarchy on a (global) grid; force_levels > 0 fixes the depth (slab mode)
+std::vector<std::pair<int64_t, int64_t>> mg_level_sizes(const fdfd_grid_t& g, double omega, const MGParams& prm, int force_levels) {
+  const double eps0 = kEps0 * g.L0, mu0 = kMu0 * g.L0;
+  std::vector<std::pair<int64_t, int64_t>> sizes;
+  int64_t nx = g.Nx, ny = g.Ny;
+  sizes.push_back({nx, ny});
+  // stop coarsening once the coarsest level is mass dominated even in vacuum (k0 h >= kh_stop): there damped Jacobi
+  // alone converges (|kappa| >> 4) and deeper levels would only add latency-bound launches
+  const double k0 = omega * std::sqrt(eps0 * mu0);
+  while ((int)sizes.size() < prm.max_levels) {
+    if (force_levels > 0 && (int)sizes.size() >= force_levels) break;
+    const double hl = std::min(grid_dx(g), grid_dy(g)) * (double)((int64_t)1 << (sizes.size() - 1));
+    if (force_levels <= 0 && prm.kh_stop > 0 && k0 * hl >= prm.kh_stop) break;
+    const int64_t cx = (nx + 1) / 2, cy = (ny + 1) / 2;
+    if (cx < prm.min_n || cy < prm.min_n || cx < 2 || cy < 2) break;
+    nx = cx; ny = cy; sizes.push_back({nx, ny});
+  }
+  return sizes;
+}
+
 // ==============================================================================================
 template <typename T> int Multigrid<T>::setup(fdfd_ctx* ctx_, const FineOp& op, const MGParams& prm_) {
   ctx = ctx_; prm = prm_; te = op.pol == FDFD_TE;
@@ -786,27 +810,33 @@ template <typename T> int Multigrid<T>::setup(fdfd_ctx* ctx_, const FineOp& op, 
   // store M scaled to O(1) coefficients (TE couplings are ~1e21 in SI-normalised units: |C|^2 overflows fp32)
   rhs_scale = (te ? eps0 : 1.0) / std::abs(op.hc.cxm[g.Nx / 2]);
   lv.clear();
-  // level sizes
-  std::vector<std::pair<int64_t, int64_t>> sizes;
-  int64_t nx = g.Nx, ny = g.Ny;
-  sizes.push_back({nx, ny});
-  // stop coarsening once the coarsest level is mass dominated even in vacuum (k0 h >= kh_stop): there damped Jacobi
-  // alone converges (|kappa| >> 4) and deeper levels would only add latency-bound launches
-  const double k0 = op.omega * std::sqrt(eps0 * mu0);
-  while ((int)sizes.size() < prm.max_levels) {
-    const double hl = std::min(grid_dx(g), grid_dy(g)) * (double)((int64_t)1 << (sizes.size() - 1));
-    if (prm.kh_stop > 0 && k0 * hl >= prm.kh_stop) break;
-    const int64_t cx = (nx + 1) / 2, cy = (ny + 1) / 2;
-    if (cx < prm.min_n || cy < prm.min_n || cx < 2 || cy < 2) break;
-    nx = cx; ny = cy; sizes.push_back({nx, ny});
-  }
+  // level sizes (slab: the depth was decided on the global grid; local rows = owned rows + 2 H_l halo rows, H_l = 2^(L-1-l),
+  // so that local coarse row lc <-> local fine row 2 lc exactly like on a whole grid)
+  const SlabInfo& sl = op.slab;
+  const fdfd_grid_t& gg = sl.on ? sl.gg : g;   // global grid: PML profile, strips
+  std::vector<std::pair<int64_t, int64_t>> sizes = mg_level_sizes(gg, op.omega, prm, sl.on ? sl.nlevels : 0);
+  const int nlev = (int)sizes.size();
+  auto Hl = [&](int l) -> int64_t { return sl.on ? ((int64_t)1 << (nlev - 1 - l)) : 0; };
+  std::vector<int64_t> nyg(nlev);              // global rows per level
+  for (int l = 0; l < nlev; ++l) { nyg[l] = sizes[l].second; if (sl.on) sizes[l].second = (sl.nyl >> l) + 2 * Hl(l); }
+  // slice a global per-row array of level l (per entries per row) to the slab's local rows (periodic wrap)
+  auto ysl = [&](const std::vector<cdh>& v, int l, int per) -> std::vector<cdh> {
+    if (!sl.on) return v;
+    const int64_t nloc = sizes[l].second, n = nyg[l], off = (sl.y0 >> l) - Hl(l);
+    std::vector<cdh> o((size_t)nloc * per);
+    for (int64_t i = 0; i < nloc; ++i) {
+      const int64_t gi = ((off + i) % n + n) % n;
+      for (int k = 0; k < per; ++k) o[(size_t)i * per + k] = v[(size_t)gi * per + k];
+    }
+    return o;
+  };
   lv.resize(sizes.size());
   // 1-D hierarchies from the reference s-factors (not inverted) at the PML frequency
   Hier1D HX, HY;
   {
     std::vector<cdh> sxf, sxb, syf, syb;
-    host_sfactor(g, 0, 1, op.omega_pml, sxf); host_sfactor(g, 0, 0, op.omega_pml, sxb);
-    host_sfactor(g, 1, 1, op.omega_pml, syf); host_sfactor(g, 1, 0, op.omega_pml, syb);
+    host_sfactor(gg, 0, 1, op.omega_pml, sxf); host_sfactor(gg, 0, 0, op.omega_pml, sxb);
+    host_sfactor(gg, 1, 1, op.omega_pml, syf); host_sfactor(gg, 1, 0, op.omega_pml, syb);
     auto EV = [&](const std::vector<cdh>& sf, const std::vector<cdh>& sb, std::vector<cdh>& E, std::vector<cdh>& V) {
       const int64_t n = (int64_t)sf.size();
       E.resize(n); V.resize(n);
@@ -831,16 +861,19 @@ template <typename T> int Multigrid<T>::setup(fdfd_ctx* ctx_, const FineOp& op, 
       const double hx = grid_dx(g) * (double)L.stride, hy = grid_dy(g) * (double)L.stride;
       hier_coefs(HX, (int)l, scale / (hx * hx), hc.cxm, hc.cxp);
       hier_coefs(HY, (int)l, scale / (hy * hy), hc.cym, hc.cyp);
+      hc.cym = ysl(hc.cym, (int)l, 1); hc.cyp = ysl(hc.cyp, (int)l, 1);
     }
     {  // transfer weights: prolongation from level l+1 (fine-indexed wl|wr) and restriction to level l+1
       std::vector<cplx<T>> pw; pw.reserve(2 * L.nx + 2 * L.ny);
-      for (auto* v : {&HX.wl[l], &HX.wr[l], &HY.wl[l], &HY.wr[l]}) for (auto& z : *v) pw.push_back(cplx<T>(T(z.real()), T(z.imag())));
+      const std::vector<cdh> wly = ysl(HY.wl[l], (int)l, 1), wry = ysl(HY.wr[l], (int)l, 1);
+      for (const std::vector<cdh>* v : {(const std::vector<cdh>*)&HX.wl[l], (const std::vector<cdh>*)&HX.wr[l], &wly, &wry}) for (auto& z : *v) pw.push_back(cplx<T>(T(z.real()), T(z.imag())));
       CUDA_TRY(ctx, L.pw.alloc(pw.size()));
       CUDA_TRY(ctx, cudaMemcpyAsync(L.pw.p, pw.data(), pw.size() * sizeof(cplx<T>), cudaMemcpyHostToDevice, ctx->stream));
       CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
       if (l + 1 < lv.size()) {
         std::vector<cplx<T>> rw; std::vector<c128> rwd;
-        for (auto* v : {&HX.R[l], &HY.R[l]}) for (auto& z : *v) { rw.push_back(cplx<T>(T(z.real()), T(z.imag()))); rwd.push_back(c128(z.real(), z.imag())); }
+        const std::vector<cdh> Ry = ysl(HY.R[l], (int)l + 1, 3);
+        for (const std::vector<cdh>* v : {(const std::vector<cdh>*)&HX.R[l], &Ry}) for (auto& z : *v) { rw.push_back(cplx<T>(T(z.real()), T(z.imag()))); rwd.push_back(c128(z.real(), z.imag())); }
         CUDA_TRY(ctx, L.rw.alloc(rw.size())); CUDA_TRY(ctx, L.rwd.alloc(rwd.size()));
         CUDA_TRY(ctx, cudaMemcpyAsync(L.rw.p, rw.data(), rw.size() * sizeof(cplx<T>), cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(ctx, cudaMemcpyAsync(L.rwd.p, rwd.data(), rwd.size() * sizeof(c128), cudaMemcpyHostToDevice, ctx->stream));
@@ -889,7 +922,15 @@ template <typename T> int Multigrid<T>::setup(fdfd_ctx* ctx_, const FineOp& op, 
       int64_t w = (npml + L.stride - 1) / L.stride + prm.pad;
       return (int)std::min<int64_t>(w, n / 2);
     };
-    L.npx = strip(g.Npml_x, L.nx); L.npy = strip(g.Npml_y, L.ny);
+    L.npx = strip(gg.Npml_x, L.nx);
+    if (!sl.on) { L.npy = strip(gg.Npml_y, L.ny); L.ys = YS{0, L.npy, (int)L.ny - L.npy, (int)L.ny}; }
+    else {  // the slab's share of the global y-strip rows [0,npy) U [NyG-npy,NyG), in local row numbers (halo rows excluded)
+      const int npyg = strip(gg.Npml_y, nyg[l]);
+      const int64_t o0 = sl.y0 >> l, o1 = o0 + (sl.nyl >> l), off = o0 - Hl((int)l);
+      auto clampi = [&](int64_t a) { return (int)(std::min(std::max(a, o0), o1) - off); };
+      L.npy = 0;
+      L.ys = YS{clampi(0), clampi(npyg), clampi(nyg[l] - npyg), clampi(nyg[l])};
+    }
     auto log2ceil = [](int64_t n) { int k = 0; while (((int64_t)1 << k) < n) ++k; return k; };
     L.Ky = log2ceil(L.ny); L.Kx = log2ceil(L.nx);
     if (L.npx > 0) {
@@ -898,27 +939,27 @@ template <typename T> int Multigrid<T>::setup(fdfd_ctx* ctx_, const FineOp& op, 
       scratch_need = std::max(scratch_need, (size_t)2 * L.npx * 6 * L.ny);
       if ((size_t)2 * L.ny * sizeof(cplx<T>) > 200 * 1024) line_scratch_need = std::max(line_scratch_need, (size_t)2 * L.npx * 2 * L.ny);
     }
-    if (L.npy > 0) {
-      CUDA_TRY(ctx, L.rys.alloc((size_t)2 * L.npy * L.nx));
-      CUDA_TRY(ctx, L.pcr_x.alloc((size_t)2 * L.npy * (2 * L.Kx + 1) * L.nx));
-      scratch_need = std::max(scratch_need, (size_t)2 * L.npy * 6 * L.nx);
-      if ((size_t)2 * L.nx * sizeof(cplx<T>) > 200 * 1024) line_scratch_need = std::max(line_scratch_need, (size_t)2 * L.npy * 2 * L.nx);
+    if (L.ys.count() > 0) {
+      CUDA_TRY(ctx, L.rys.alloc((size_t)L.ys.count() * L.nx));
+      CUDA_TRY(ctx, L.pcr_x.alloc((size_t)L.ys.count() * (2 * L.Kx + 1) * L.nx));
+      scratch_need = std::max(scratch_need, (size_t)L.ys.count() * 6 * L.nx);
+      if ((size_t)2 * L.nx * sizeof(cplx<T>) > 200 * 1024) line_scratch_need = std::max(line_scratch_need, (size_t)L.ys.count() * 2 * L.nx);
     }
   }
   CUDA_TRY(ctx, spare.alloc((size_t)g.Nx * g.Ny));
-  for (auto& L : lv) { const int64_t nmax = std::max(L.nx, L.ny); if ((size_t)2 * nmax * sizeof(cplx<T>) > 200 * 1024) line_scratch_need = std::max(line_scratch_need, (size_t)(2 * L.npx + 2 * L.npy) * 2 * nmax); }
+  for (auto& L : lv) { const int64_t nmax = std::max(L.nx, L.ny); if ((size_t)2 * nmax * sizeof(cplx<T>) > 200 * 1024) line_scratch_need = std::max(line_scratch_need, (size_t)(2 * L.npx + L.ys.count()) * 2 * nmax); }
   CUDA_TRY(ctx, pcr_scratch.alloc(scratch_need));
   if (line_scratch_need) CUDA_TRY(ctx, line_scratch.alloc(line_scratch_need));
   for (size_t l = 0; l < lv.size(); ++l) {
     MGLevel<T>& L = lv[l];
     if (L.npx > 0) {
-      if (te) k_pcr_setup<T, true><<<2 * L.npx, 256, 0, ctx->stream>>>(L.view(), 0, L.npx, L.Ky, pcr_scratch.p, L.pcr_y.p);
-      else k_pcr_setup<T, false><<<2 * L.npx, 256, 0, ctx->stream>>>(L.view(), 0, L.npx, L.Ky, pcr_scratch.p, L.pcr_y.p);
+      if (te) k_pcr_setup<T, true><<<2 * L.npx, 256, 0, ctx->stream>>>(L.view(), 0, L.npx, L.ys, L.Ky, pcr_scratch.p, L.pcr_y.p);
+      else k_pcr_setup<T, false><<<2 * L.npx, 256, 0, ctx->stream>>>(L.view(), 0, L.npx, L.ys, L.Ky, pcr_scratch.p, L.pcr_y.p);
       KLAUNCH(ctx);
     }
-    if (L.npy > 0) {
-      if (te) k_pcr_setup<T, true><<<2 * L.npy, 256, 0, ctx->stream>>>(L.view(), 1, L.npy, L.Kx, pcr_scratch.p, L.pcr_x.p);
-      else k_pcr_setup<T, false><<<2 * L.npy, 256, 0, ctx->stream>>>(L.view(), 1, L.npy, L.Kx, pcr_scratch.p, L.pcr_x.p);
+    if (L.ys.count() > 0) {
+      if (te) k_pcr_setup<T, true><<<L.ys.count(), 256, 0, ctx->stream>>>(L.view(), 1, L.npy, L.ys, L.Kx, pcr_scratch.p, L.pcr_x.p);
+      else k_pcr_setup<T, false><<<L.ys.count(), 256, 0, ctx->stream>>>(L.view(), 1, L.npy, L.ys, L.Kx, pcr_scratch.p, L.pcr_x.p);
       KLAUNCH(ctx);
     }
     CUDA_TRY(ctx, cudaGetLastError());
@@ -988,23 +1029,43 @@ template <typename T> int Multigrid<T>::smooth(int l, bool zero, bool prolong) {
   static const bool use_tile = []() { const char* e = getenv("FDFD_MG_KERNELS"); return !(e && std::string(e) == "march"); }();
   dim3 tgrid((unsigned)((L.nx + kTX - 1) / kTX), (unsigned)((L.ny + kTY - 1) / kTY));
   dim3 mgrid((unsigned)((L.nx + kMW * kMWarps - 1) / (kMW * kMWarps)), (unsigned)((L.ny + kMRows - 1) / kMRows));
-#define SM2(TEV, ZV, PV) k_smooth2<T, TEV, ZV, PV><<<grid, kMgThreads, 0, ctx->stream>>>(op, L.u.p, L.f.p, out, L.rxs.p, L.rys.p, L.npx, L.npy, wj, pv, done)
-#define SMT(TEV, PV) do { if (use_tile) k_smooth2_tile<T, TEV, PV><<<tgrid, kTileThreads, 0, ctx->stream>>>(op, L.u.p, L.f.p, out, L.rxs.p, L.rys.p, L.npx, L.npy, wj, pv, done); \
-    else k_smooth2_march<T, TEV, PV><<<mgrid, 32 * kMWarps, 0, ctx->stream>>>(op, L.u.p, L.f.p, out, L.rxs.p, L.rys.p, L.npx, L.npy, wj, pv, done); } while (0)
+#define SM2(TEV, ZV, PV) k_smooth2<T, TEV, ZV, PV><<<grid, kMgThreads, 0, ctx->stream>>>(op, L.u.p, L.f.p, out, L.rxs.p, L.rys.p, L.npx, L.ys, wj, pv, done)
+#define SMT(TEV, PV) do { if (use_tile) k_smooth2_tile<T, TEV, PV><<<tgrid, kTileThreads, 0, ctx->stream>>>(op, L.u.p, L.f.p, out, L.rxs.p, L.rys.p, L.npx, L.ys, wj, pv, done); \
+    else k_smooth2_march<T, TEV, PV><<<mgrid, 32 * kMWarps, 0, ctx->stream>>>(op, L.u.p, L.f.p, out, L.rxs.p, L.rys.p, L.npx, L.ys, wj, pv, done); } while (0)
   if (te) { if (zero) SM2(true, true, false); else if (prolong) SMT(true, true); else SMT(true, false); }
   else    { if (zero) SM2(false, true, false); else if (prolong) SMT(false, true); else SMT(false, false); }
 #undef SM2
 #undef SMT
   KLAUNCH(ctx);
   if (!zero) std::swap(L.u.p, L.tmp.p);
-  const int nlines = 2 * L.npx + 2 * L.npy;
+  const int nlines = 2 * L.npx + L.ys.count();
   if (nlines > 0) {
     const int64_t nmax = std::max(L.nx, L.ny);
     const size_t smem = (size_t)2 * nmax * sizeof(cplx<T>);
     const bool use_g = smem > 200 * 1024;
     const int threads = (int)std::min<int64_t>(1024, std::max<int64_t>(32, ((nmax + 31) / 32) * 32));
-    k_lines2<T><<<nlines, threads, use_g ? 0 : smem, ctx->stream>>>(L.nx, L.ny, L.npx, L.npy, L.Ky, L.Kx, L.pcr_y.p, L.pcr_x.p,
+    k_lines2<T><<<nlines, threads, use_g ? 0 : smem, ctx->stream>>>(L.nx, L.ny, L.npx, L.ys, L.Ky, L.Kx, L.pcr_y.p, L.pcr_x.p,
                                                                    L.rxs.p, L.rys.p, L.u.p, wl, use_g ? line_scratch.p : nullptr, done);
+    KLAUNCH(ctx);
+  }
+  CUDA_TRY(ctx, cudaGetLastError());
+  return FDFD_OK;
+}
+
+template <typename T> int Multigrid<T>::restrict_residual(int l) {
+  MGLevel<T>& L = lv[l];
+  MGLevel<T>& C = lv[l + 1];
+  {
+    static const bool use_tile = []() { const char* e = getenv("FDFD_MG_KERNELS"); return !(e && std::string(e) == "march"); }();
+    if (use_tile) {
+      dim3 grid((unsigned)((C.nx + kCX - 1) / kCX), (unsigned)((C.ny + kCY - 1) / kCY));
+      if (te) k_restrict_tile<T, true><<<grid, kTileThreads, 0, ctx->stream>>>(L.view(), L.u.p, L.f.p, C.nx, C.ny, L.rw.p, L.rw.p + 3 * C.nx, C.f.p, done);
+      else k_restrict_tile<T, false><<<grid, kTileThreads, 0, ctx->stream>>>(L.view(), L.u.p, L.f.p, C.nx, C.ny, L.rw.p, L.rw.p + 3 * C.nx, C.f.p, done);
+    } else {
+      dim3 grid((unsigned)((L.nx + kRWc * kMWarps - 1) / (kRWc * kMWarps)), (unsigned)((C.ny + kRCRows - 1) / kRCRows));
+      if (te) k_restrict_march<T, true><<<grid, 32 * kMWarps, 0, ctx->stream>>>(L.view(), L.u.p, L.f.p, C.nx, C.ny, L.rw.p, L.rw.p + 3 * C.nx, C.f.p, done);
+      else k_restrict_march<T, false><<<grid, 32 * kMWarps, 0, ctx->stream>>>(L.view(), L.u.p, L.f.p, C.nx, C.ny, L.rw.p, L.rw.p + 3 * C.nx, C.f.p, done);
+    }
     KLAUNCH(ctx);
   }
   CUDA_TRY(ctx, cudaGetLastError());
@@ -1020,19 +1081,7 @@ template <typename T> int Multigrid<T>::cycle(int l, bool zero, int kind) {
   }
   for (int s = 0; s < std::max(1, prm.nu1); ++s) FDFD_TRY(smooth(l, zero && s == 0));
   MGLevel<T>& C = lv[l + 1];
-  {
-    static const bool use_tile = []() { const char* e = getenv("FDFD_MG_KERNELS"); return !(e && std::string(e) == "march"); }();
-    if (use_tile) {
-      dim3 grid((unsigned)((C.nx + kCX - 1) / kCX), (unsigned)((C.ny + kCY - 1) / kCY));
-      if (te) k_restrict_tile<T, true><<<grid, kTileThreads, 0, ctx->stream>>>(L.view(), L.u.p, L.f.p, C.nx, C.ny, L.rw.p, L.rw.p + 3 * C.nx, C.f.p, done);
-      else k_restrict_tile<T, false><<<grid, kTileThreads, 0, ctx->stream>>>(L.view(), L.u.p, L.f.p, C.nx, C.ny, L.rw.p, L.rw.p + 3 * C.nx, C.f.p, done);
-    } else {
-      dim3 grid((unsigned)((L.nx + kRWc * kMWarps - 1) / (kRWc * kMWarps)), (unsigned)((C.ny + kRCRows - 1) / kRCRows));
-      if (te) k_restrict_march<T, true><<<grid, 32 * kMWarps, 0, ctx->stream>>>(L.view(), L.u.p, L.f.p, C.nx, C.ny, L.rw.p, L.rw.p + 3 * C.nx, C.f.p, done);
-      else k_restrict_march<T, false><<<grid, 32 * kMWarps, 0, ctx->stream>>>(L.view(), L.u.p, L.f.p, C.nx, C.ny, L.rw.p, L.rw.p + 3 * C.nx, C.f.p, done);
-    }
-    KLAUNCH(ctx);
-  }
+  FDFD_TRY(restrict_residual(l));
   if (kind == 2 && l < prm.wdepth) {
     FDFD_TRY(cycle(l + 1, true, 2));
     FDFD_TRY(cycle(l + 1, false, 2));

@@ -19,8 +19,12 @@
 #pragma once
 #include "device_ops.cuh"
 
+// rows of the y-direction PML strip as two ranges [a0,a1) U [b0,b1)
+struct YS { int a0 = 0, a1 = 0, b0 = 0, b1 = 0; int count() const { return (a1 - a0) + (b1 - b0); } };
+
 template <typename T> struct MGLevel {
   int64_t nx = 0, ny = 0, stride = 1;
+  YS ys;                      // y-strip rows of this level (single GPU: [0,npy) U [ny-npy,ny))
   int npx = 0, npy = 0;       // strip half-widths: columns [0,npx) U [nx-npx,nx), rows likewise
   int Kx = 0, Ky = 0;         // PCR steps of x-lines (length nx) / y-lines (length ny)
   DevBuf<cplx<T>> c1d, mass, gx, gy;
@@ -48,6 +52,8 @@ struct MGParams {
   double kh_stop = 4.0;
 };
 
+std::vector<std::pair<int64_t, int64_t>> mg_level_sizes(const fdfd_grid_t& g, double omega, const MGParams& prm, int force_levels);
+
 template <typename T> struct Multigrid {
   fdfd_ctx* ctx = nullptr;
   bool te = false;
@@ -66,8 +72,9 @@ template <typename T> struct Multigrid {
   cplx<T>* rhs() { return lv[0].f.p; }
   int levels() const { return (int)lv.size(); }
 
- private:
+  // building blocks (public: the slab driver runs them in lock step over several slabs with halo exchanges between)
   int cycle(int l, bool zero, int kind);
   int smooth(int l, bool zero, bool prolong = false);
   int smooth_classic(int l, bool zero);
+  int restrict_residual(int l);
 };

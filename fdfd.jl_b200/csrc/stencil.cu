@@ -46,7 +46,7 @@ template <typename TI, bool TE, int NDOT, int ROWS, int MINB, bool HINT>
 __global__ void __launch_bounds__(kApplyThreads, MINB)
 k_apply(OpView<double> op, const TI* __restrict__ x, c128* __restrict__ y, const c128* __restrict__ d0,
         c128* __restrict__ partials, const int* __restrict__ done, const TI* __restrict__ xm1, const TI* __restrict__ xp1,
-        const c128* __restrict__ deps, double hw) {
+        const c128* __restrict__ deps, double hw, int64_t row_lo, int64_t row_hi) {
   if (done && *done) return;
   const int64_t Nx = op.nx, Ny = op.ny;
   const int64_t ix = blockIdx.x * (int64_t)kApplyThreads + threadIdx.x;
@@ -68,6 +68,7 @@ k_apply(OpView<double> op, const TI* __restrict__ x, c128* __restrict__ y, const
       const int64_t iyp = iy + 1 == Ny ? 0 : iy + 1;
       const int64_t n = ix + Nx * iy;
       const c128 un = ldx(x, ix + Nx * iyp);
+      if (iy < row_lo || iy >= row_hi) { y[n] = c128(0.0, 0.0); us = uc; uc = un; continue; }  // halo row of a slab
       const c128 uw = ldx(x, ixm + Nx * iy), ue = ldx(x, ixp + Nx * iy);
       c128 W = cw, E = ce, S = op.cym[iy], Nn = op.cyp[iy], m;
       if (TE) {
@@ -184,12 +185,49 @@ static int apply_variant() {
 }
 static int variant_rows(int v) { static const int rows[8] = {4, 8, 16, 4, 8, 16, 32, 8}; return rows[v]; }
 
+int FineOp::build_slab(fdfd_ctx* ctx, const fdfd_grid_t& gg, int ordering_, double omega_, const fdfd_c128* eps_local_any,
+                       int64_t y0, int64_t nyl, int nlevels) {
+  pol = FDFD_TM; ordering = ordering_; omega = omega_; omega_pml = omega_;
+  slab.on = true; slab.gg = gg; slab.y0 = y0; slab.nyl = nyl; slab.nlevels = nlevels; slab.H = (int64_t)1 << (nlevels - 1);
+  ARG_CHECK(ctx, nyl % ((int64_t)1 << (nlevels - 1)) == 0 && y0 % ((int64_t)1 << (nlevels - 1)) == 0 && gg.Ny % ((int64_t)1 << (nlevels - 1)) == 0,
+            "slab rows must be divisible by 2^(levels-1)");
+  const int64_t nloc = nyl + 2 * slab.H;
+  g = gg; g.Ny = nloc; g.Npml_y = 0;
+  const double dyg = grid_dy(gg);
+  g.y0 = gg.y0 + dyg * (double)slab.yoff(); g.y1 = g.y0 + dyg * (double)nloc;
+  const int64_t N = g.Nx * nloc;
+  const double eps0 = kEps0 * gg.L0, mu0 = kMu0 * gg.L0;
+  Coef1D gh;
+  host_coef_fine(gg, omega_pml, ordering, 1.0 / mu0, gh);
+  hc.cxm = gh.cxm; hc.cxp = gh.cxp; hc.cym.resize(nloc); hc.cyp.resize(nloc);
+  for (int64_t i = 0; i < nloc; ++i) {
+    const int64_t gi = ((slab.yoff() + i) % gg.Ny + gg.Ny) % gg.Ny;
+    hc.cym[i] = gh.cym[gi]; hc.cyp[i] = gh.cyp[gi];
+  }
+  CUDA_TRY(ctx, c1d.alloc(2 * g.Nx + 2 * nloc));
+  std::vector<std::complex<double>> pack;
+  pack.insert(pack.end(), hc.cxm.begin(), hc.cxm.end()); pack.insert(pack.end(), hc.cxp.begin(), hc.cxp.end());
+  pack.insert(pack.end(), hc.cym.begin(), hc.cym.end()); pack.insert(pack.end(), hc.cyp.begin(), hc.cyp.end());
+  CUDA_TRY(ctx, cudaMemcpyAsync(c1d.p, pack.data(), pack.size() * sizeof(c128), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, eps.alloc(N));
+  FDFD_TRY(fdfd_copy_in(ctx, eps.p, eps_local_any, N * sizeof(c128)));
+  CUDA_TRY(ctx, mass.alloc(N));
+  const int threads = 256;
+  const int blocks = (int)std::min<int64_t>((N + threads - 1) / threads, (int64_t)ctx->num_sms * 16);
+  k_setup_tm<<<blocks, threads, 0, ctx->stream>>>(N, omega * omega * eps0, eps.p, mass.p);
+  KLAUNCH(ctx);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return FDFD_OK;
+}
+
 template <typename TI, bool TE, int NDOT, int ROWS, int MINB, bool HINT>
 static int launch_apply_v(fdfd_ctx* ctx, const OpView<double>& op, const TI* x, c128* y, const DotSpec& ds, const Coupling* cpl) {
   dim3 grid((unsigned)((op.nx + kApplyThreads - 1) / kApplyThreads), (unsigned)((op.ny + ROWS - 1) / ROWS));
   if (ds.nblocks_out) *ds.nblocks_out = (int)(grid.x * grid.y);
   k_apply<TI, TE, NDOT, ROWS, MINB, HINT><<<grid, kApplyThreads, 0, ctx->stream>>>(op, x, y, ds.d0, ds.partials, ds.done,
-      cpl ? (const TI*)cpl->xm1 : nullptr, cpl ? (const TI*)cpl->xp1 : nullptr, cpl ? cpl->deps : nullptr, cpl ? cpl->hw : 0.0);
+      cpl ? (const TI*)cpl->xm1 : nullptr, cpl ? (const TI*)cpl->xp1 : nullptr, cpl ? cpl->deps : nullptr, cpl ? cpl->hw : 0.0,
+      ds.row_lo, ds.row_hi < 0 ? op.ny : ds.row_hi);
   KLAUNCH(ctx);
   CUDA_TRY(ctx, cudaGetLastError());
   return FDFD_OK;
@@ -235,7 +273,14 @@ int launch_recover(fdfd_ctx* ctx, const FineOp& op, const c128* u, int forward, 
   const double mu0 = kMu0 * g.L0;
   // inverse s-factors of the requested difference direction, frozen at the operator's omega
   std::vector<std::complex<double>> sx, sy;
-  host_sfactor(g, 0, forward, op.omega_pml, sx); host_sfactor(g, 1, forward, op.omega_pml, sy);
+  if (op.slab.on) {  // s-factors of the GLOBAL grid, y-array sliced to the slab's local rows
+    std::vector<std::complex<double>> syg;
+    host_sfactor(op.slab.gg, 0, forward, op.omega_pml, sx); host_sfactor(op.slab.gg, 1, forward, op.omega_pml, syg);
+    sy.resize(g.Ny);
+    for (int64_t i = 0; i < g.Ny; ++i) sy[i] = syg[((op.slab.yoff() + i) % op.slab.gg.Ny + op.slab.gg.Ny) % op.slab.gg.Ny];
+  } else {
+    host_sfactor(g, 0, forward, op.omega_pml, sx); host_sfactor(g, 1, forward, op.omega_pml, sy);
+  }
   for (auto& z : sx) z = 1.0 / z;
   for (auto& z : sy) z = 1.0 / z;
   DevBuf<c128> ds;

@@ -193,6 +193,41 @@ int fdfd_problem_flux_x(fdfd_problem* p, double center_x, double center_y, doubl
  * other pixels keep the value already in eps_r (host or device buffer, (Nx,Ny)). */
 int fdfd_rasterize(fdfd_ctx* ctx, const fdfd_grid_t* g, int nshapes, const double* shapes7, fdfd_c128* eps_r);
 
+/* ---- one large grid split into row slabs (BASELINE config 5) -------------------------------------------
+ * The reference has no parallel path at all (its solve is one `lu(A)\b`, src/solver/solver.jl:35); this is the sharded
+ * form of solve(d::Device, TM) (src/solver/driven.jl:4-59) for grids that do not fit / are too slow on one GPU.
+ * The global grid is cut into `nranks` contiguous y-slabs of Ny/nranks rows (x stays the fast, contiguous index); slab
+ * r owns global rows [r*Ny/nranks, (r+1)*Ny/nranks).  Each slab runs the same BiCGSTAB + multigrid on its rows; the
+ * only exchanges are (1) ring halo rows between neighbouring slabs (the operators are periodic, grid.jl:147,150, so the
+ * ring closes) after every stencil-type kernel and (2) one sum of <= 4 doubles over the ranks per Krylov dot product.
+ *
+ * Communicators.  FDFD_COMM_NCCL: one process per GPU; rank 0 calls fdfd_comm_unique_id, the host program broadcasts
+ * the FDFD_COMM_ID_BYTES bytes (torch.distributed / MPI / a file) and every rank calls fdfd_comm_create_nccl.
+ * FDFD_COMM_THREADS: all slabs inside one process, one host thread per slab (any mix of GPUs, including all on one
+ * GPU): fdfd_comm_group_create once, fdfd_comm_create_threads per rank.  Calls on a communicator are collective:
+ * every rank must make the same calls in the same order. */
+enum { FDFD_COMM_THREADS = 0, FDFD_COMM_NCCL = 1 };
+#define FDFD_COMM_ID_BYTES 128
+typedef struct fdfd_comm fdfd_comm;
+typedef struct fdfd_comm_group fdfd_comm_group;
+int fdfd_comm_unique_id(void* id_bytes);
+int fdfd_comm_create_nccl(fdfd_ctx* ctx, int nranks, int rank, const void* id_bytes, fdfd_comm** out);
+int fdfd_comm_group_create(int nranks, fdfd_comm_group** out);
+void fdfd_comm_group_destroy(fdfd_comm_group* grp);
+int fdfd_comm_create_threads(fdfd_comm_group* grp, int rank, fdfd_comm** out);
+void fdfd_comm_destroy(fdfd_comm* comm);
+/* rows owned by `rank` of `nranks`: *y0 = first global row, *nrows = Ny/nranks.  Host-only helper (no GPU needed). */
+int fdfd_slab_rows(const fdfd_grid_t* g, int nranks, int rank, int64_t* y0, int64_t* nrows);
+/* the solve.  g is the GLOBAL grid; eps_r_rows, src_rows: this rank's owned rows, (Nx, nrows) x fastest (a contiguous
+ * row range of the global column-major arrays); fields_rows: (Nx, nrows, 3).  info is identical on every rank except
+ * for the timings.  Ny must be divisible by nranks and the slab height by 2^(multigrid levels - 1); the hierarchy is
+ * truncated to the deepest depth that allows it. */
+int fdfd_solve_driven_slab(fdfd_ctx* ctx, fdfd_comm* comm, const fdfd_grid_t* g, double omega,
+                           const fdfd_c128* eps_r_rows, const fdfd_c128* src_rows, const fdfd_solve_opts_t* opts,
+                           fdfd_c128* fields_rows, fdfd_info_t* info);
+/* counters of the communicator since creation: exchanges, allreduces, bytes sent by this rank */
+int fdfd_comm_stats(fdfd_comm* comm, int64_t* n_exchange, int64_t* n_allreduce, int64_t* bytes_sent);
+
 /* host-only test hook (no GPU needed): the small dense complex Hessenberg eigen-solver behind the Ritz pairs of
  * fdfd_eigenfrequency.  H, evecs: column-major n x n; evals: n. */
 int fdfd_debug_hess_eig(int n, const fdfd_c128* H, fdfd_c128* evals, fdfd_c128* evecs);
