@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--ref-grid", dest="ref_n", type=int, default=512, help="grid edge of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep", type=int, default=4, help="frequencies per GPU per step, solved concurrently (one stream each)")
+    ap.add_argument("--mode", default="sweep", choices=["sweep", "slab"],
+                    help="sweep (default, the metric): disjoint frequencies per GPU, weak scaling.  slab: ONE --grid^2 solve split "
+                         "into row slabs over the GPUs (halo exchange + allreduce over NCCL), strong scaling (BASELINE config 5)")
     return ap.parse_args()
 
 
@@ -299,9 +302,107 @@ def b200_arm(args):
         dist.destroy_process_group()
 
 
+def slab_arm(args):
+    """One grid, row slabs over the ranks (SURVEY §8e second mode): step = one fdfd_solve_driven_slab call on every rank."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    import fdfd_jl_b200 as fdfd
+    from importlib import import_module
+    wl = import_module("fdfd_jl_b200.workloads")
+    slab = import_module("fdfd_jl_b200.slab")
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.Stream()
+    ctx = fdfd.Context(local, stream=stream.cuda_stream)
+    comm = slab.SlabComm.nccl(ctx, rank, world)
+    n = args.n
+    g0 = fdfd.Grid(0.02, [15, 15], [0.0, n * 0.02], [0.0, n * 0.02])
+    y0, nr = slab.slab_rows(g0, world, rank)
+    g, omega, eps_rows, src_rows = wl.synthetic_tm_device(fdfd, n, n, density=args.density, rows=(y0, nr))
+    gc = g.as_c()
+    opts = fdfd.default_opts()
+    M = n * nr
+    eps_h = torch.from_numpy(np.asfortranarray(eps_rows).ravel(order="F").copy()).pin_memory()
+    src_h = torch.from_numpy(np.asfortranarray(src_rows).ravel(order="F").copy()).pin_memory()
+    eps_d, src_d = eps_h.cuda(), src_h.cuda()
+    fields_d = torch.empty(3 * M, dtype=torch.complex128, device="cuda")
+    fields_h = torch.empty(3 * M, dtype=torch.complex128).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(e, s_, f):
+        info = fdfd.Info()
+        code = fdfd.lib().fdfd_solve_driven_slab(ctx.handle, comm.handle, C.byref(gc), omega, fdfd.ptr(e), fdfd.ptr(s_), C.byref(opts),
+                                                 fdfd.ptr(f), C.byref(info))
+        fdfd.check(code, ctx.handle)
+        return info.asdict()
+
+    infos = []
+    for _ in range(args.warmup):
+        step(eps_d.data_ptr(), src_d.data_ptr(), fields_d.data_ptr())
+    barrier()
+    l0 = ctx.launch_count()
+    with ClockSampler(local) as clk:
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            infos.append(step(eps_d.data_ptr(), src_d.data_ptr(), fields_d.data_ptr()))
+            stream.synchronize()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t_res = e0.elapsed_time(e1) * 1e-3
+    launches = ctx.launch_count() - l0
+    barrier()
+    e2 = torch.cuda.Event(enable_timing=True); e3 = torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    step(eps_h.data_ptr(), src_h.data_ptr(), fields_h.data_ptr())
+    stream.synchronize()
+    e3.record(stream)
+    torch.cuda.synchronize()
+    tt = torch.tensor([t_res, e2.elapsed_time(e3) * 1e-3], dtype=torch.float64, device="cuda")
+    ok = torch.tensor([1 if all(i["flag"] == 0 and i["relres"] <= 1e-10 for i in infos) else 0], device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    t_max, t_e2e = float(tt[0].item()), float(tt[1].item())
+    st = comm.stats()
+    if rank == 0:
+        i0 = infos[-1]
+        line = {"metric": f"solves_per_sec_{n}x{n}_TM_slab_to_1e-10", "value": args.steps / t_max, "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_max / args.steps * 1e3, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+                "config": {"workload": f"ONE synthetic TM device {n}x{n} (same map family as the sweep workload) split into {world} row slabs of "
+                                       f"{nr} rows; step = setup + BiCGSTAB/multigrid to 1e-10 + H recovery on every slab",
+                           "grid": [n, n], "parallelism": f"y-slabs x{world}: ring halo exchange (ncclSend/Recv) after every stencil-type kernel, "
+                                                          "one 4-double allreduce per dot product, iteration replayed as one CUDA graph",
+                           "l2": "inputs larger than L2"},
+                "converged": bool(ok.item()),
+                "solve": {"iters": [i["iters"] for i in infos], "relres": [i["relres"] for i in infos],
+                          "krylov_ms": [round(i["solve_ms"], 1) for i in infos], "setup_ms": [round(i["setup_ms"], 1) for i in infos],
+                          "mg_levels": i0["mg_levels"], "ms_per_iteration": i0["solve_ms"] / max(1, i0["iters"])},
+                "e2e": {"value": 1.0 / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * M * 16 * world, "d2h_bytes_per_step": 3 * M * 16 * world, "steps": 1},
+                "gpu_launches": int(launches), "comm_per_rank_captured": st, "clocks": clk.summary()}
+        print(json.dumps(line), flush=True)
+    comm.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         reference_arm(a)
+    elif a.mode == "slab":
+        slab_arm(a)
     else:
         b200_arm(a)

@@ -59,7 +59,7 @@ struct FineOp {
 struct Coupling { const void* xm1 = nullptr; const void* xp1 = nullptr; const c128* deps = nullptr; double hw = 0.0; };
 struct DotSpec {
   int ndot = 0; const c128* d0 = nullptr; c128* partials = nullptr; int* nblocks_out = nullptr; const int* done = nullptr;
-  int64_t row_lo = 0, row_hi = -1;  // slab mode: rows outside [row_lo,row_hi) are written as 0 and excluded from the dots
+  int64_t row_lo = 0, row_hi = -1;  // slab mode: only rows [row_lo,row_hi) are computed (halo rows of y are left untouched)
 };
 int launch_apply(fdfd_ctx* ctx, const OpView<double>& op, bool te, const void* x, bool x_is_f32, c128* y, const DotSpec& ds,
                  const Coupling* cpl = nullptr);

@@ -76,7 +76,7 @@ struct SlabSolver {
   KrylovOps make_ops() {
     KrylovOps k;
     SlabSolver* S = this;
-    k.nab = apply_num_blocks(Nx, nloc);
+    k.nab = apply_num_blocks(Nx, nyl);   // the apply launches over the owned rows only
     k.prec_f32 = true; k.prec_rhs = mg.rhs(); k.fscale = mg.rhs_scale;
     k.apply = [S](const void* x, bool x_f32, c128* y, const DotSpec& ds) -> int {
       DotSpec d = ds; d.row_lo = S->H; d.row_hi = S->H + S->nyl;

@@ -50,7 +50,7 @@ k_apply(OpView<double> op, const TI* __restrict__ x, c128* __restrict__ y, const
   if (done && *done) return;
   const int64_t Nx = op.nx, Ny = op.ny;
   const int64_t ix = blockIdx.x * (int64_t)kApplyThreads + threadIdx.x;
-  const int64_t iy0 = blockIdx.y * (int64_t)ROWS;
+  const int64_t iy0 = row_lo + blockIdx.y * (int64_t)ROWS;   // a slab launches over its owned rows [row_lo, row_hi) only
   double acc[NDOT > 0 ? 2 * NDOT : 1];
 #pragma unroll
   for (int k = 0; k < (NDOT > 0 ? 2 * NDOT : 1); ++k) acc[k] = 0.0;
@@ -64,11 +64,10 @@ k_apply(OpView<double> op, const TI* __restrict__ x, c128* __restrict__ y, const
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
       const int64_t iy = iy0 + r;
-      if (iy >= Ny) break;
+      if (iy >= row_hi) break;
       const int64_t iyp = iy + 1 == Ny ? 0 : iy + 1;
       const int64_t n = ix + Nx * iy;
       const c128 un = ldx(x, ix + Nx * iyp);
-      if (iy < row_lo || iy >= row_hi) { y[n] = c128(0.0, 0.0); us = uc; uc = un; continue; }  // halo row of a slab
       const c128 uw = ldx(x, ixm + Nx * iy), ue = ldx(x, ixp + Nx * iy);
       c128 W = cw, E = ce, S = op.cym[iy], Nn = op.cyp[iy], m;
       if (TE) {
@@ -223,11 +222,12 @@ int FineOp::build_slab(fdfd_ctx* ctx, const fdfd_grid_t& gg, int ordering_, doub
 
 template <typename TI, bool TE, int NDOT, int ROWS, int MINB, bool HINT>
 static int launch_apply_v(fdfd_ctx* ctx, const OpView<double>& op, const TI* x, c128* y, const DotSpec& ds, const Coupling* cpl) {
-  dim3 grid((unsigned)((op.nx + kApplyThreads - 1) / kApplyThreads), (unsigned)((op.ny + ROWS - 1) / ROWS));
+  const int64_t row_hi = ds.row_hi < 0 ? op.ny : ds.row_hi;
+  dim3 grid((unsigned)((op.nx + kApplyThreads - 1) / kApplyThreads), (unsigned)((row_hi - ds.row_lo + ROWS - 1) / ROWS));
   if (ds.nblocks_out) *ds.nblocks_out = (int)(grid.x * grid.y);
   k_apply<TI, TE, NDOT, ROWS, MINB, HINT><<<grid, kApplyThreads, 0, ctx->stream>>>(op, x, y, ds.d0, ds.partials, ds.done,
       cpl ? (const TI*)cpl->xm1 : nullptr, cpl ? (const TI*)cpl->xp1 : nullptr, cpl ? cpl->deps : nullptr, cpl ? cpl->hw : 0.0,
-      ds.row_lo, ds.row_hi < 0 ? op.ny : ds.row_hi);
+      ds.row_lo, row_hi);
   KLAUNCH(ctx);
   CUDA_TRY(ctx, cudaGetLastError());
   return FDFD_OK;

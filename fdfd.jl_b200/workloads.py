@@ -9,15 +9,20 @@ import numpy as np
 OMEGA_200THZ = 2 * math.pi * 200e12
 
 
-def synthetic_tm_device(fdfd, Nx, Ny, dh=0.02, npml=15, seed=0, density=1.0 / 40.0):
+def synthetic_tm_device(fdfd, Nx, Ny, dh=0.02, npml=15, seed=0, density=1.0 / 40.0, rows=None):
     """Vacuum + eps=12 straight waveguide (0.3 um wide, along x through the centre, runtests.jl:26) + a seeded
     set of eps in [2, 12.25] cylinders/boxes; x-normal line source at ix = npml + 10 (device.jl:103-104).
-    dh = 0.02 um = lambda0/75 at 200 THz (notebook cell 14)."""
+    dh = 0.02 um = lambda0/75 at 200 THz (notebook cell 14).
+    rows=(y0, n): rasterise only global rows [y0, y0+n) (slab-sharded runs: every rank builds its own rows of the same
+    map); returns (grid, omega, eps_rows, src_rows) with (Nx, n) arrays instead of a Device."""
     g = fdfd.Grid(dh, [npml, npml], [0.0, Nx * dh], [0.0, Ny * dh])
     assert g.N == (Nx, Ny)
-    d = fdfd.Device(g, OMEGA_200THZ)
-    xs, ys = fdfd.xc(g)[:, None], fdfd.yc(g)[None, :]
-    eps = np.ones((Nx, Ny))
+    yall = fdfd.yc(g)
+    if rows is not None:
+        yall = yall[rows[0]:rows[0] + rows[1]]
+    xall = fdfd.xc(g)
+    xs, ys = xall[:, None], yall[None, :]
+    eps = np.ones((Nx, len(yall)))
     rng = np.random.default_rng(seed)
     Lx, Ly = Nx * dh, Ny * dh
     nshape = max(4, int(Lx * Ly * density))
@@ -26,11 +31,26 @@ def synthetic_tm_device(fdfd, Nx, Ny, dh=0.02, npml=15, seed=0, density=1.0 / 40
         e = rng.uniform(2, 12.25)
         if k % 2 == 0:
             r = rng.uniform(0.3, 1.5)
-            eps[(xs - cx) ** 2 + (ys - cy) ** 2 <= r * r] = e
+            hx = hy = r
         else:
             wx, wy = rng.uniform(0.3, 3), rng.uniform(0.3, 3)
-            eps[(np.abs(xs - cx) <= wx / 2) & (np.abs(ys - cy) <= wy / 2)] = e
-    eps[:, np.abs(fdfd.yc(g) - Ly / 2) <= 0.15] = 12.0
+            hx, hy = wx / 2, wy / 2
+        # only the bounding box of the shape is touched (the map has hundreds of shapes at 16384^2)
+        i0, i1 = np.searchsorted(xall, cx - hx - dh), np.searchsorted(xall, cx + hx + dh)
+        j0, j1 = np.searchsorted(yall, cy - hy - dh), np.searchsorted(yall, cy + hy + dh)
+        if i0 >= i1 or j0 >= j1:
+            continue
+        sx, sy, sub = xs[i0:i1], ys[:, j0:j1], eps[i0:i1, j0:j1]
+        if k % 2 == 0:
+            sub[(sx - cx) ** 2 + (sy - cy) ** 2 <= r * r] = e
+        else:
+            sub[(np.abs(sx - cx) <= wx / 2) & (np.abs(sy - cy) <= wy / 2)] = e
+    eps[:, np.abs(yall - Ly / 2) <= 0.15] = 12.0
+    if rows is not None:
+        src = np.zeros(eps.shape, dtype=np.complex128)
+        src[npml + 10, :] = 1j
+        return g, OMEGA_200THZ, eps.astype(np.complex128), src
+    d = fdfd.Device(g, OMEGA_200THZ)
     d.eps_r = eps.astype(np.complex128)
     d.src[npml + 10, :] = 1j
     return d
