@@ -157,3 +157,22 @@ def solve_slabs_threads(d, nslabs: int, devices=None, **kw):
         if e is not None:
             raise e
     return FieldTM(d.grid, d.omega[0], data, infos[0]), infos
+
+
+def gather_field(grid, omega, rows_data, rank, world, info=None, group=None):
+    """Assemble the full FieldTM on rank 0 from every rank's (Nx, nrows, 3) rows (torch.distributed gather; any backend).
+    Other ranks get None.  Only for grids whose (Nx,Ny,3) field fits one host; large runs keep the rows sharded."""
+    from . import FieldTM
+    if world == 1:
+        return FieldTM(grid, omega, np.asfortranarray(rows_data), info)
+    import torch.distributed as dist
+    bucket = [None] * world if rank == 0 else None
+    dist.gather_object((rank, np.ascontiguousarray(rows_data)), bucket, dst=0, group=group)
+    if rank != 0:
+        return None
+    Nx, Ny = grid.N
+    data = np.empty((Nx, Ny, 3), dtype=np.complex128, order="F")
+    for r, part in bucket:
+        y0, n = slab_rows(grid, world, r)
+        data[:, y0:y0 + n, :] = part
+    return FieldTM(grid, omega, data, info)
