@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--ref-grid", dest="ref_n", type=int, default=512, help="grid edge of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep", type=int, default=4, help="frequencies per GPU per step, solved concurrently (one stream each)")
+    ap.add_argument("--no-e2e", action="store_true", help="slab mode: skip the host-buffer (end-to-end) repetition of the solve")
     ap.add_argument("--mode", default="sweep", choices=["sweep", "slab"],
                     help="sweep (default, the metric): disjoint frequencies per GPU, weak scaling.  slab: ONE --grid^2 solve split "
                          "into row slabs over the GPUs (halo exchange + allreduce over NCCL), strong scaling (BASELINE config 5)")
@@ -365,7 +366,8 @@ def slab_arm(args):
     barrier()
     e2 = torch.cuda.Event(enable_timing=True); e3 = torch.cuda.Event(enable_timing=True)
     e2.record(stream)
-    step(eps_h.data_ptr(), src_h.data_ptr(), fields_h.data_ptr())
+    if not args.no_e2e:
+        step(eps_h.data_ptr(), src_h.data_ptr(), fields_h.data_ptr())
     stream.synchronize()
     e3.record(stream)
     torch.cuda.synchronize()
@@ -390,7 +392,8 @@ def slab_arm(args):
                 "solve": {"iters": [i["iters"] for i in infos], "relres": [i["relres"] for i in infos],
                           "krylov_ms": [round(i["solve_ms"], 1) for i in infos], "setup_ms": [round(i["setup_ms"], 1) for i in infos],
                           "mg_levels": i0["mg_levels"], "ms_per_iteration": i0["solve_ms"] / max(1, i0["iters"])},
-                "e2e": {"value": 1.0 / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * M * 16 * world, "d2h_bytes_per_step": 3 * M * 16 * world, "steps": 1},
+                "e2e": None if args.no_e2e else {"value": 1.0 / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * M * 16 * world,
+                                                 "d2h_bytes_per_step": 3 * M * 16 * world, "steps": 1},
                 "gpu_launches": int(launches), "comm_per_rank_captured": st, "clocks": clk.summary()}
         print(json.dumps(line), flush=True)
     comm.close()

@@ -15,6 +15,7 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
@@ -33,7 +34,7 @@ NcclApi* nccl_api() {
     if (!api.h) { api.err = std::string("cannot load libnccl.so.2: ") + dlerror(); return; }
 #define BIND(field, sym) do { *(void**)(&api.field) = dlsym(api.h, sym); if (!api.field) { api.err = std::string("libnccl lacks ") + sym; api.h = nullptr; return; } } while (0)
     BIND(GetUniqueId, "ncclGetUniqueId"); BIND(CommInitRank, "ncclCommInitRank"); BIND(CommDestroy, "ncclCommDestroy");
-    BIND(AllReduce, "ncclAllReduce"); BIND(Send, "ncclSend"); BIND(Recv, "ncclRecv");
+    BIND(AllReduce, "ncclAllReduce"); BIND(AllGather, "ncclAllGather"); BIND(Send, "ncclSend"); BIND(Recv, "ncclRecv");
     BIND(GroupStart, "ncclGroupStart"); BIND(GroupEnd, "ncclGroupEnd"); BIND(GetErrorString, "ncclGetErrorString");
 #undef BIND
   });
@@ -91,6 +92,26 @@ int fdfd_comm::exchange(fdfd_ctx* ctx, void* lo_halo, void* hi_halo, const void*
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   grp->barrier();
   if (grp->failed) { fdfd_set_error(ctx, "slab exchange: another rank failed or timed out"); return FDFD_ERR_CUDA; }
+  return FDFD_OK;
+}
+
+int fdfd_comm::allgather(fdfd_ctx* ctx, const void* send, void* recv, size_t bytes) {
+  ++n_allgather; bytes_sent += (int64_t)bytes * (nranks - 1);
+  cudaStream_t st = ctx->stream;
+  if (nranks == 1) { CUDA_TRY(ctx, cudaMemcpyAsync(recv, send, bytes, cudaMemcpyDeviceToDevice, st)); return FDFD_OK; }
+  if (kind == FDFD_COMM_NCCL) {
+    NCCL_TRY(ctx, nccl_api()->AllGather(send, recv, bytes, ncclChar, (ncclComm_t)nccl, st));
+    return FDFD_OK;
+  }
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  grp->lo_src[rank] = send;
+  grp->barrier();
+  if (grp->failed) { fdfd_set_error(ctx, "slab allgather: another rank failed or timed out"); return FDFD_ERR_CUDA; }
+  for (int r = 0; r < nranks; ++r)
+    CUDA_TRY(ctx, cudaMemcpyAsync((char*)recv + (size_t)r * bytes, grp->lo_src[r], bytes, cudaMemcpyDefault, st));
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  grp->barrier();
+  if (grp->failed) { fdfd_set_error(ctx, "slab allgather: another rank failed or timed out"); return FDFD_ERR_CUDA; }
   return FDFD_OK;
 }
 

@@ -32,12 +32,15 @@ struct fdfd_comm {
   void* nccl = nullptr;        // ncclComm_t
   CommGroup* grp = nullptr;
   double* h_pinned = nullptr;  // 4 doubles, thread transport
-  int64_t n_exchange = 0, n_allreduce = 0, bytes_sent = 0;
+  int64_t n_exchange = 0, n_allreduce = 0, n_allgather = 0, bytes_sent = 0;
   bool capturable() const { return kind == FDFD_COMM_NCCL || nranks == 1; }
 
   // my `lo_src` rows go to the previous slab's high halo, my `hi_src` rows to the next slab's low halo;
   // `lo_halo` receives the previous slab's hi_src, `hi_halo` the next slab's lo_src.  Stream-ordered on ctx->stream.
   int exchange(fdfd_ctx* ctx, void* lo_halo, void* hi_halo, const void* lo_src, const void* hi_src, size_t bytes);
+  // recv (nranks * bytes) <- concatenation in rank order of every rank's `send` (bytes each): the agglomerated coarse
+  // level of the slab multigrid (slabs are equal contiguous row ranges, so rank order IS global row order)
+  int allgather(fdfd_ctx* ctx, const void* send, void* recv, size_t bytes);
   // in-place sum over the ranks of 4 doubles in device memory; every rank ends with bit-identical values
   int allreduce_sum4(fdfd_ctx* ctx, double* dev4);
 };

@@ -14,17 +14,17 @@ template <typename T> struct OpView {
   cplx<T> mass_const;
 };
 
-// fp64 fine-grid operator resident in HBM
 // a y-slab of a global grid: owned global rows [y0, y0+nyl), stored with H halo rows on each side
 struct SlabInfo {
   bool on = false;
   fdfd_grid_t gg{};        // the global grid
   int64_t y0 = 0, nyl = 0; // owned rows (fine level)
-  int64_t H = 0;           // fine-level halo width = 2^(nlevels-1)
+  int64_t H = 0;           // fine-level halo width, a multiple of 2^(nlevels-1); level l keeps H >> l halo rows
   int nlevels = 0;         // multigrid depth, decided on the global grid
   int64_t yoff() const { return y0 - H; }  // global row of local row 0
 };
 
+// fp64 fine-grid operator resident in HBM
 struct FineOp {
   fdfd_grid_t g{};         // grid the arrays are sized for (slab: Nx x (nyl + 2H), same cell size as the global grid)
   SlabInfo slab;
@@ -42,7 +42,7 @@ struct FineOp {
             double omega_pml = 0.0);
   // slab of the global grid gg: eps_local_any holds the (nyl + 2H) x Nx local rows (halo rows included, periodic wrap)
   int build_slab(fdfd_ctx* ctx, const fdfd_grid_t& gg, int ordering, double omega, const fdfd_c128* eps_local_any,
-                 int64_t y0, int64_t nyl, int nlevels);
+                 int64_t y0, int64_t nyl, int nlevels, int64_t halo);
   OpView<double> view() const {
     OpView<double> v;
     v.nx = g.Nx; v.ny = g.Ny;

@@ -802,8 +802,9 @@ std::vector<std::pair<int64_t, int64_t>> mg_level_sizes(const fdfd_grid_t& g, do
 }
 
 // ==============================================================================================
-template <typename T> int Multigrid<T>::setup(fdfd_ctx* ctx_, const FineOp& op, const MGParams& prm_) {
-  ctx = ctx_; prm = prm_; te = op.pol == FDFD_TE;
+template <typename T> int Multigrid<T>::setup(fdfd_ctx* ctx_, const FineOp& op, const MGParams& prm_, int first_level,
+                                               const c128* eps_first) {
+  ctx = ctx_; prm = prm_; te = op.pol == FDFD_TE; first = first_level;
   const fdfd_grid_t& g = op.g;
   const double eps0 = kEps0 * g.L0, mu0 = kMu0 * g.L0;
   const double scale = te ? 1.0 : 1.0 / mu0;
@@ -816,7 +817,7 @@ template <typename T> int Multigrid<T>::setup(fdfd_ctx* ctx_, const FineOp& op, 
   const fdfd_grid_t& gg = sl.on ? sl.gg : g;   // global grid: PML profile, strips
   std::vector<std::pair<int64_t, int64_t>> sizes = mg_level_sizes(gg, op.omega, prm, sl.on ? sl.nlevels : 0);
   const int nlev = (int)sizes.size();
-  auto Hl = [&](int l) -> int64_t { return sl.on ? ((int64_t)1 << (nlev - 1 - l)) : 0; };
+  auto Hl = [&](int l) -> int64_t { return sl.on ? (sl.H >> l) : 0; };
   std::vector<int64_t> nyg(nlev);              // global rows per level
   for (int l = 0; l < nlev; ++l) { nyg[l] = sizes[l].second; if (sl.on) sizes[l].second = (sl.nyl >> l) + 2 * Hl(l); }
   // slice a global per-row array of level l (per entries per row) to the slab's local rows (periodic wrap)
@@ -854,6 +855,7 @@ template <typename T> int Multigrid<T>::setup(fdfd_ctx* ctx_, const FineOp& op, 
     MGLevel<T>& L = lv[l];
     L.nx = sizes[l].first; L.ny = sizes[l].second; L.stride = (int64_t)1 << l;
     const int64_t N = L.nx * L.ny;
+    if ((int)l < first_level) continue;   // partial hierarchy (levels >= first_level only): nothing resident above it
     // 1-D coefficients
     Coef1D hc;
     if (l == 0) hc = op.hc;
@@ -888,10 +890,11 @@ template <typename T> int Multigrid<T>::setup(fdfd_ctx* ctx_, const FineOp& op, 
     // eps of this level
     const c128* eps_l = nullptr;
     const int threads = 256;
-    if (l == 0) eps_l = op.eps.p;
+    if ((int)l == first_level && first_level > 0) eps_l = eps_first;
+    else if (l == 0) eps_l = op.eps.p;
     else {
       CUDA_TRY(ctx, L.eps.alloc(N));
-      const c128* eps_f = l == 1 ? op.eps.p : lv[l - 1].eps.p;
+      const c128* eps_f = ((int)l - 1 == first_level && first_level > 0) ? eps_first : (l == 1 ? op.eps.p : lv[l - 1].eps.p);
       const int blocks = (int)std::min<int64_t>((N + threads - 1) / threads, (int64_t)ctx->num_sms * 16);
       k_restrict_eps<<<blocks, threads, 0, ctx->stream>>>(lv[l - 1].nx, lv[l - 1].ny, L.nx, L.ny, lv[l - 1].rwd.p,
                                                         lv[l - 1].rwd.p + 3 * L.nx, eps_f, L.eps.p);
@@ -924,12 +927,22 @@ template <typename T> int Multigrid<T>::setup(fdfd_ctx* ctx_, const FineOp& op, 
     };
     L.npx = strip(gg.Npml_x, L.nx);
     if (!sl.on) { L.npy = strip(gg.Npml_y, L.ny); L.ys = YS{0, L.npy, (int)L.ny - L.npy, (int)L.ny}; }
-    else {  // the slab's share of the global y-strip rows [0,npy) U [NyG-npy,NyG), in local row numbers (halo rows excluded)
+    else {
+      // every LOCAL row (halo rows included) whose global row lies in the y-strip [0,npy) U [NyG-npy,NyG) gets the x-line
+      // relaxation, so a halo row is smoothed exactly as its owner smooths it (x-lines are never cut).  With the periodic
+      // closure the strip rows form at most two runs of local rows (around the low and the high end of the slab).
       const int npyg = strip(gg.Npml_y, nyg[l]);
-      const int64_t o0 = sl.y0 >> l, o1 = o0 + (sl.nyl >> l), off = o0 - Hl((int)l);
-      auto clampi = [&](int64_t a) { return (int)(std::min(std::max(a, o0), o1) - off); };
+      const int64_t nloc = L.ny, n = nyg[l], off = (sl.y0 >> l) - Hl((int)l);
+      int runs[3][2]; int nr = 0; bool in = false;
+      for (int64_t i = 0; i <= nloc; ++i) {
+        const int64_t gi = ((off + i) % n + n) % n;
+        const bool s = i < nloc && npyg > 0 && (gi < npyg || gi >= n - npyg);
+        if (s && !in) { if (nr < 3) runs[nr][0] = (int)i; in = true; }
+        if (!s && in) { if (nr < 3) runs[nr][1] = (int)i; ++nr; in = false; }
+      }
+      ARG_CHECK(ctx, nr <= 2, "internal: the y-strip rows of a slab form more than two runs");
       L.npy = 0;
-      L.ys = YS{clampi(0), clampi(npyg), clampi(nyg[l] - npyg), clampi(nyg[l])};
+      L.ys = YS{nr > 0 ? runs[0][0] : 0, nr > 0 ? runs[0][1] : 0, nr > 1 ? runs[1][0] : 0, nr > 1 ? runs[1][1] : 0};
     }
     auto log2ceil = [](int64_t n) { int k = 0; while (((int64_t)1 << k) < n) ++k; return k; };
     L.Ky = log2ceil(L.ny); L.Kx = log2ceil(L.nx);
@@ -946,7 +959,7 @@ template <typename T> int Multigrid<T>::setup(fdfd_ctx* ctx_, const FineOp& op, 
       if ((size_t)2 * L.nx * sizeof(cplx<T>) > 200 * 1024) line_scratch_need = std::max(line_scratch_need, (size_t)L.ys.count() * 2 * L.nx);
     }
   }
-  CUDA_TRY(ctx, spare.alloc((size_t)g.Nx * g.Ny));
+  if (first_level == 0) CUDA_TRY(ctx, spare.alloc((size_t)g.Nx * g.Ny));
   for (auto& L : lv) { const int64_t nmax = std::max(L.nx, L.ny); if ((size_t)2 * nmax * sizeof(cplx<T>) > 200 * 1024) line_scratch_need = std::max(line_scratch_need, (size_t)(2 * L.npx + L.ys.count()) * 2 * nmax); }
   CUDA_TRY(ctx, pcr_scratch.alloc(scratch_need));
   if (line_scratch_need) CUDA_TRY(ctx, line_scratch.alloc(line_scratch_need));

@@ -66,7 +66,10 @@ template <typename T> struct Multigrid {
   const int* done = nullptr;     // optional device flag: kernels early-exit once the Krylov loop has converged
 
   // build hierarchy for the operator `op` (fine eps_r resident in op.eps)
-  int setup(fdfd_ctx* ctx, const FineOp& op, const MGParams& prm);
+  // first_level > 0 builds only levels >= first_level (the agglomerated coarse part of a slab-sharded solve): `op` then
+  // needs its host-side members only and eps_first is the level-first_level eps_r resident in HBM
+  int setup(fdfd_ctx* ctx, const FineOp& op, const MGParams& prm, int first_level = 0, const c128* eps_first = nullptr);
+  int first = 0;
   // u0 = approx M^-1 f0 where f0 = lv[0].f (already filled).  Result pointer returned in *out (lv[0].u or .tmp)
   int apply(const cplx<T>** out);
   cplx<T>* rhs() { return lv[0].f.p; }
