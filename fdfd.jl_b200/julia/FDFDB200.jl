@@ -106,4 +106,35 @@ function eigenfrequency_b200(d::AbstractDevice{2}, pol::Polarization, nev::Int; 
     return (ω, [F(d.grid, ω[i], out[:, :, :, i]) for i = 1:nev])
 end
 
+# ---- one large grid split into row slabs over several GPUs (include/fdfd_b200.h, "row slabs"; csrc/slab.cu) -------------
+# One Julia process per GPU (e.g. MPI.jl or Distributed.jl workers).  Rank 0 makes the 128-byte NCCL id, the host program
+# broadcasts it (MPI.Bcast!, a file, ...), every rank creates its communicator and calls solve_slab_b200 with the SAME
+# device; each rank gets back its own rows of FieldTM.data.  The halo exchange and the Krylov allreduce run inside the
+# library over NCCL (NVLink), never through Julia.
+nccl_unique_id() = (id = zeros(UInt8, 128); check(ccall((:fdfd_comm_unique_id, LIB), Cint, (Ptr{UInt8},), id)); id)
+
+function slab_comm(id::Vector{UInt8}, nranks::Int, rank::Int)
+    c = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:fdfd_comm_create_nccl, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}, Ref{Ptr{Cvoid}}), ctx(), nranks, rank, id, c))
+    return c[]
+end
+
+function slab_rows(g::Grid{2}, nranks::Int, rank::Int)
+    y0 = Ref{Int64}(0); n = Ref{Int64}(0)
+    check(ccall((:fdfd_slab_rows, LIB), Cint, (Ref{CGrid}, Cint, Cint, Ref{Int64}, Ref{Int64}), CGrid(g), nranks, rank, y0, n))
+    return (y0[] + 1):(y0[] + n[])          # 1-based row range owned by `rank`
+end
+
+"solve(d, TM) of one frequency with the grid cut into `nranks` row slabs; returns the (Nx, nrows, 3) rows of this rank"
+function solve_slab_b200(d::Device{2}, comm::Ptr{Cvoid}, nranks::Int, rank::Int)
+    rows = slab_rows(d.grid, nranks, rank); (Nx, _) = size(d.grid)
+    ϵ = ComplexF64.(d.ϵᵣ[:, rows]); src = ComplexF64.(d.src[:, rows]); out = Array{ComplexF64}(undef, Nx, length(rows), 3)
+    opts = COpts(); info = CInfo()
+    GC.@preserve ϵ src out check(ccall((:fdfd_solve_driven_slab, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ref{CGrid}, Float64, Ptr{ComplexF64}, Ptr{ComplexF64}, Ref{COpts}, Ptr{ComplexF64}, Ref{CInfo}),
+        ctx(), comm, CGrid(d.grid), d.ω[1], ϵ, src, opts, out, info))
+    @info "fdfd_b200 slab solve" rank iters=info.iters relres=info.relres
+    return out
+end
+
 end # module
