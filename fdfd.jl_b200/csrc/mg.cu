@@ -101,128 +101,52 @@ __global__ void k_restrict_eps(int64_t nxf, int64_t nyf, int64_t nxc, int64_t ny
   }
 }
 
-// ---- PCR setup: one CTA per line, fp64, global scratch (a,b,c ping-pong) -------------------------
-// mode 0: y-lines (column ix = strip_index(c)), a=S, c=N.  mode 1: x-lines (row iy), a=W, c=E.  Wrap couplings
-// are dropped (they link the two deepest PML cells and stay in the lagged part of the splitting).
+// ---- PCR setup: one CTA per (line, segment), fp64, global scratch (a,b,c ping-pong) -------------------------
+// mode 0: y-lines (column ix = strip_index(c)), a=S, c=N.  mode 1: x-lines (row iy), a=W, c=E.  Couplings are cut at
+// the segment ends (at the ends of the line these are the periodic wrap couplings: they link the two deepest PML cells
+// and stay in the lagged part of the splitting).
 template <typename T, bool TE>
-__global__ void k_pcr_setup(OpView<T> op, int mode, int np, YS ys, int K, c128* __restrict__ scratch, cplx<T>* __restrict__ mult) {
+__global__ void k_pcr_setup(OpView<T> op, int mode, int np, YS ys, LineSeg sg, c128* __restrict__ scratch, cplx<T>* __restrict__ mult) {
   const int64_t nx = op.nx, ny = op.ny;
-  const int64_t n = mode == 0 ? ny : nx;
-  const int64_t c = blockIdx.x;
+  const int64_t c = blockIdx.x / sg.nseg;
+  const int j = blockIdx.x % sg.nseg;
+  const int lo = sg.lo(j), n = sg.hi(j) - lo, K = sg.K, SL = sg.SL;
   const int64_t fixed = mode == 0 ? strip_index(c, nx, np) : (int64_t)ys_row(ys, (int)c);
-  c128* a0 = scratch + (size_t)c * 6 * n; c128* b0 = a0 + n; c128* c0 = b0 + n;
-  c128* a1 = c0 + n; c128* b1 = a1 + n; c128* c1 = b1 + n;
-  cplx<T>* alpha = mult + (size_t)c * (2 * K + 1) * n;
-  cplx<T>* gamma = alpha + (size_t)K * n;
-  cplx<T>* binv = gamma + (size_t)K * n;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-    const int64_t ix = mode == 0 ? fixed : i, iy = mode == 0 ? i : fixed;
+  c128* a0 = scratch + (size_t)blockIdx.x * 6 * SL; c128* b0 = a0 + SL; c128* c0 = b0 + SL;
+  c128* a1 = c0 + SL; c128* b1 = a1 + SL; c128* c1 = b1 + SL;
+  cplx<T>* alpha = mult + (size_t)blockIdx.x * (2 * K + 1) * SL;
+  cplx<T>* gamma = alpha + (size_t)K * SL;
+  cplx<T>* binv = gamma + (size_t)K * SL;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int64_t ix = mode == 0 ? fixed : lo + i, iy = mode == 0 ? lo + i : fixed;
     const int64_t ixp = ix + 1 == nx ? 0 : ix + 1, iyp = iy + 1 == ny ? 0 : iy + 1;
     cplx<T> W, E, S, Nn, C;
     row_coefs<T, TE>(op, ix, iy, ixp, iyp, W, E, S, Nn, C);
-    c128 lo = mode == 0 ? c128(S) : c128(W), hi = mode == 0 ? c128(Nn) : c128(E);
-    if (i == 0) lo = c128(0.0, 0.0);
-    if (i == n - 1) hi = c128(0.0, 0.0);
-    a0[i] = lo; b0[i] = c128(C); c0[i] = hi;
+    c128 l = mode == 0 ? c128(S) : c128(W), h = mode == 0 ? c128(Nn) : c128(E);
+    if (i == 0) l = c128(0.0, 0.0);
+    if (i == n - 1) h = c128(0.0, 0.0);
+    a0[i] = l; b0[i] = c128(C); c0[i] = h;
   }
   __syncthreads();
   for (int k = 0; k < K; ++k) {
-    const int64_t s = (int64_t)1 << k;
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const int s = 1 << k;
+    for (int i = threadIdx.x; i < SL; i += blockDim.x) {
       c128 al(0.0, 0.0), ga(0.0, 0.0);
-      c128 bn = b0[i], an(0.0, 0.0), cn(0.0, 0.0);
-      if (i >= s) { al = -cdiv(a0[i], b0[i - s]); bn += al * c0[i - s]; an = al * a0[i - s]; }
-      if (i + s < n) { ga = -cdiv(c0[i], b0[i + s]); bn += ga * a0[i + s]; cn = ga * c0[i + s]; }
-      a1[i] = an; b1[i] = bn; c1[i] = cn;
-      alpha[(size_t)k * n + i] = cplx<T>(al); gamma[(size_t)k * n + i] = cplx<T>(ga);
+      if (i < n) {
+        c128 bn = b0[i], an(0.0, 0.0), cn(0.0, 0.0);
+        if (i >= s) { al = -cdiv(a0[i], b0[i - s]); bn += al * c0[i - s]; an = al * a0[i - s]; }
+        if (i + s < n) { ga = -cdiv(c0[i], b0[i + s]); bn += ga * a0[i + s]; cn = ga * c0[i + s]; }
+        a1[i] = an; b1[i] = bn; c1[i] = cn;
+      }
+      alpha[(size_t)k * SL + i] = cplx<T>(al); gamma[(size_t)k * SL + i] = cplx<T>(ga);
     }
     __syncthreads();
     c128* t;
     t = a0; a0 = a1; a1 = t; t = b0; b0 = b1; b1 = t; t = c0; c0 = c1; c1 = t;
   }
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) binv[i] = cplx<T>(crecip(b0[i]));
+  for (int i = threadIdx.x; i < SL; i += blockDim.x) binv[i] = i < n ? cplx<T>(crecip(b0[i])) : cplx<T>(T(0), T(0));
 }
 
-// ---- smoother, phase 1: point Jacobi outside the strips + residual capture on the strip columns ----------
-template <typename T, bool TE, bool ZERO>
-__global__ void __launch_bounds__(kMgThreads)
-k_smooth_pt(OpView<T> op, const cplx<T>* __restrict__ u, const cplx<T>* __restrict__ f, cplx<T>* __restrict__ out,
-            cplx<T>* __restrict__ rxs, int npx, int npy, T wj, const int* __restrict__ done) {
-  if (done && *done) return;
-  const int64_t nx = op.nx, ny = op.ny;
-  const int64_t ix = blockIdx.x * (int64_t)kMgThreads + threadIdx.x;
-  if (ix >= nx) return;
-  const bool xs = in_strip(ix, nx, npx);
-#pragma unroll
-  for (int r = 0; r < kMgRows; ++r) {
-    const int64_t iy = blockIdx.y * (int64_t)kMgRows + r;
-    if (iy >= ny) break;
-    const int64_t n = ix + nx * iy;
-    const bool ys = in_strip(iy, ny, npy);
-    const cplx<T> u0 = ZERO ? cplx<T>(T(0), T(0)) : u[n];
-    if (ys && !xs) { out[n] = u0; continue; }
-    cplx<T> C, res;
-    if (ZERO) {
-      res = f[n];
-      if (!xs) {
-        const int64_t ixp = ix + 1 == nx ? 0 : ix + 1, iyp = iy + 1 == ny ? 0 : iy + 1;
-        cplx<T> W, E, S, Nn;
-        row_coefs<T, TE>(op, ix, iy, ixp, iyp, W, E, S, Nn, C);
-      }
-    } else {
-      res = residual_at<T, TE>(op, u, f, ix, iy, &C);
-    }
-    if (xs) { rxs[strip_line(ix, nx, npx) * ny + iy] = res; out[n] = u0; }
-    else out[n] = u0 + wj * cdiv(res, C);
-  }
-}
-
-// ---- smoother, phase 3: residual on the strip rows (after the y-line update) ---------------------------
-template <typename T, bool TE>
-__global__ void k_resid_rows(OpView<T> op, const cplx<T>* __restrict__ u, const cplx<T>* __restrict__ f,
-                             cplx<T>* __restrict__ rys, int npy, const int* __restrict__ done) {
-  if (done && *done) return;
-  const int64_t nx = op.nx, ny = op.ny;
-  const int64_t ix = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int64_t c = blockIdx.y;
-  if (ix >= nx) return;
-  const int64_t iy = strip_index(c, ny, npy);
-  rys[c * nx + ix] = residual_at<T, TE>(op, u, f, ix, iy, nullptr);
-}
-
-// ---- line solves: PCR on the right-hand side with precomputed multipliers ------------------------------
-// one CTA per line; d ping-pongs in shared memory (or a global scratch when the line is too long)
-template <typename T>
-__global__ void k_lines(int64_t n, int K, const cplx<T>* __restrict__ mult, const cplx<T>* __restrict__ rbuf,
-                        cplx<T>* __restrict__ out, int mode, int64_t nx, int64_t ny, int np, T wl,
-                        cplx<T>* __restrict__ gscratch, const int* __restrict__ done) {
-  if (done && *done) return;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int64_t c = blockIdx.x;
-  cplx<T>* d0 = gscratch ? gscratch + (size_t)c * 2 * n : reinterpret_cast<cplx<T>*>(smem_raw);
-  cplx<T>* d1 = d0 + n;
-  const cplx<T>* alpha = mult + (size_t)c * (2 * K + 1) * n;
-  const cplx<T>* gamma = alpha + (size_t)K * n;
-  const cplx<T>* binv = gamma + (size_t)K * n;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) d0[i] = rbuf[c * n + i];
-  __syncthreads();
-  for (int k = 0; k < K; ++k) {
-    const int64_t s = (int64_t)1 << k;
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-      cplx<T> v = d0[i];
-      if (i >= s) v += alpha[(size_t)k * n + i] * d0[i - s];
-      if (i + s < n) v += gamma[(size_t)k * n + i] * d0[i + s];
-      d1[i] = v;
-    }
-    __syncthreads();
-    cplx<T>* t = d0; d0 = d1; d1 = t;
-  }
-  const int64_t fixed = strip_index(c, mode == 0 ? nx : ny, np);
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-    const int64_t idx = mode == 0 ? fixed + nx * i : i + nx * fixed;
-    out[idx] += wl * (d0[i] * binv[i]);
-  }
-}
 
 // =====================================================================================================
 // Fused smoother (2 launches per sweep instead of 4; the coarse levels are launch-latency bound):
@@ -600,82 +524,58 @@ k_restrict_march(OpView<T> op, const cplx<T>* __restrict__ u, const cplx<T>* __r
   }
 }
 
+constexpr int kLineMaxK = 10;   // segments are at most 640 points long
+
 template <typename T>
-__global__ void k_lines2(int64_t nx, int64_t ny, int npx, YS ys, int Ky, int Kx, const cplx<T>* __restrict__ mult_y,
+__global__ void k_lines2(int64_t nx, int64_t ny, int npx, YS ys, LineSeg sy, LineSeg sx, const cplx<T>* __restrict__ mult_y,
                          const cplx<T>* __restrict__ mult_x, const cplx<T>* __restrict__ rxs, const cplx<T>* __restrict__ rys,
-                         cplx<T>* __restrict__ out, T wl, cplx<T>* __restrict__ gscratch, const int* __restrict__ done) {
+                         cplx<T>* __restrict__ out, T wl, const int* __restrict__ done) {
   if (done && *done) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const bool ymode = (int)blockIdx.x < 2 * npx;       // y-line of a strip column, else x-line of a strip row
-  const int c = ymode ? blockIdx.x : blockIdx.x - 2 * npx;
-  const int n = (int)(ymode ? ny : nx);
-  const int K = ymode ? Ky : Kx;
-  const int64_t nmax = nx > ny ? nx : ny;
-  cplx<T>* d0 = gscratch ? gscratch + (size_t)blockIdx.x * 2 * nmax : reinterpret_cast<cplx<T>*>(smem_raw);
-  cplx<T>* d1 = d0 + n;
-  const cplx<T>* mult = ymode ? mult_y : mult_x;
-  const cplx<T>* alpha = mult + (size_t)c * (2 * K + 1) * n;
-  const cplx<T>* gamma = alpha + (size_t)K * n;
-  const cplx<T>* binv = gamma + (size_t)K * n;
-  const cplx<T>* rbuf = (ymode ? rxs : rys) + (size_t)c * n;
-  constexpr int EPT = 4;  // elements per thread held in registers
-  const int nt = blockDim.x, tid = threadIdx.x;
-  for (int i = tid; i < n; i += nt) d0[i] = rbuf[i];
-  if (n <= EPT * nt) {
-    // the multipliers of step k+1 are fetched while step k runs out of shared memory: the PCR steps are otherwise a
-    // chain of (global-load latency + barrier) with nothing to overlap
-    cplx<T> a_cur[EPT], g_cur[EPT], a_nxt[EPT], g_nxt[EPT];
+  const int nby = 2 * npx * sy.nseg;
+  const bool ymode = (int)blockIdx.x < nby;           // y-line of a strip column, else x-line of a strip row
+  const int b = ymode ? blockIdx.x : blockIdx.x - nby;
+  const LineSeg sg = ymode ? sy : sx;
+  const int c = b / sg.nseg, j = b % sg.nseg;
+  const int lo = sg.lo(j), n = sg.hi(j) - lo, K = sg.K, SL = sg.SL;
+  cplx<T>* d0 = reinterpret_cast<cplx<T>*>(smem_raw);
+  cplx<T>* d1 = d0 + SL;
+  const cplx<T>* alpha = (ymode ? mult_y : mult_x) + (size_t)b * (2 * K + 1) * SL;
+  const cplx<T>* gamma = alpha + (size_t)K * SL;
+  const cplx<T>* binv = gamma + (size_t)K * SL;
+  const cplx<T>* rbuf = (ymode ? rxs : rys) + (size_t)c * sg.n + lo;
+  const int i = threadIdx.x;              // one line point per thread
+  const bool act = i < n;
+  // every multiplier of this point is fetched up front (one load latency instead of one per PCR step)
+  cplx<T> al[kLineMaxK], ga[kLineMaxK];
+  cplx<T> bi(T(0), T(0));
+  if (act) {
+    d0[i] = rbuf[i];
 #pragma unroll
-    for (int e = 0; e < EPT; ++e) {
-      const int i = tid + e * nt;
-      if (i < n && K > 0) { a_cur[e] = alpha[i]; g_cur[e] = gamma[i]; }
-    }
-    __syncthreads();
-    for (int k = 0; k < K; ++k) {
+    for (int k = 0; k < kLineMaxK; ++k) if (k < K) { al[k] = alpha[(size_t)k * SL + i]; ga[k] = gamma[(size_t)k * SL + i]; }
+    bi = binv[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kLineMaxK; ++k) {
+    if (k < K) {
       const int s = 1 << k;
-      if (k + 1 < K) {
-#pragma unroll
-        for (int e = 0; e < EPT; ++e) {
-          const int i = tid + e * nt;
-          if (i < n) { a_nxt[e] = alpha[(size_t)(k + 1) * n + i]; g_nxt[e] = gamma[(size_t)(k + 1) * n + i]; }
-        }
-      }
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) {
-        const int i = tid + e * nt;
-        if (i < n) {
-          cplx<T> v = d0[i];
-          if (i >= s) v += a_cur[e] * d0[i - s];
-          if (i + s < n) v += g_cur[e] * d0[i + s];
-          d1[i] = v;
-        }
-      }
-      __syncthreads();
-      cplx<T>* t = d0; d0 = d1; d1 = t;
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) { a_cur[e] = a_nxt[e]; g_cur[e] = g_nxt[e]; }
-    }
-  } else {
-    __syncthreads();
-    for (int k = 0; k < K; ++k) {
-      const int s = 1 << k;
-      for (int i = tid; i < n; i += nt) {
+      if (act) {
         cplx<T> v = d0[i];
-        if (i >= s) v += alpha[(size_t)k * n + i] * d0[i - s];
-        if (i + s < n) v += gamma[(size_t)k * n + i] * d0[i + s];
+        if (i >= s) v += al[k] * d0[i - s];
+        if (i + s < n) v += ga[k] * d0[i + s];
         d1[i] = v;
       }
       __syncthreads();
       cplx<T>* t = d0; d0 = d1; d1 = t;
     }
   }
+  const int gi = lo + i;                  // position on the line
+  if (!act || gi < sg.core_lo(j) || gi >= sg.core_hi(j)) return;
+  if (ymode && ys_in(ys, gi)) return;     // corners belong to the x-lines
   const int fixed = ymode ? (int)strip_index(c, nx, npx) : ys_row(ys, c);
-  const int inx = (int)nx;
-  for (int i = tid; i < n; i += nt) {
-    if (ymode && ys_in(ys, i)) continue;  // corners belong to the x-lines
-    const int64_t idx = ymode ? (int64_t)fixed + (int64_t)inx * i : (int64_t)i + (int64_t)inx * fixed;
-    out[idx] += wl * (d0[i] * binv[i]);
-  }
+  const int64_t idx = ymode ? (int64_t)fixed + nx * (int64_t)gi : (int64_t)gi + nx * (int64_t)fixed;
+  out[idx] += wl * (d0[i] * bi);
 }
 
 // ---- residual + restriction (coarse-point-centric).  r_c(I,J) = sum RX[I][a] RY[J][b] r(xi[a], yi[b]) with
@@ -850,7 +750,7 @@ template <typename T> int Multigrid<T>::setup(fdfd_ctx* ctx_, const FineOp& op, 
     EV(sxf, sxb, Ex, Vx); EV(syf, syb, Ey, Vy);
     build_hier1d(Ex, Vx, (int)lv.size(), HX); build_hier1d(Ey, Vy, (int)lv.size(), HY);
   }
-  size_t scratch_need = 0, line_scratch_need = 0;
+  size_t scratch_need = 0;
   for (size_t l = 0; l < lv.size(); ++l) {
     MGLevel<T>& L = lv[l];
     L.nx = sizes[l].first; L.ny = sizes[l].second; L.stride = (int64_t)1 << l;
@@ -944,95 +844,55 @@ template <typename T> int Multigrid<T>::setup(fdfd_ctx* ctx_, const FineOp& op, 
       L.npy = 0;
       L.ys = YS{nr > 0 ? runs[0][0] : 0, nr > 0 ? runs[0][1] : 0, nr > 1 ? runs[1][0] : 0, nr > 1 ? runs[1][1] : 0};
     }
-    auto log2ceil = [](int64_t n) { int k = 0; while (((int64_t)1 << k) < n) ++k; return k; };
-    L.Ky = log2ceil(L.ny); L.Kx = log2ceil(L.nx);
+    auto make_seg = [](int64_t n) {
+      LineSeg g; g.n = (int)n;
+      int Lc = 256, O = 128;
+      if (const char* e = getenv("FDFD_MG_LINE_SEG")) { const int v = atoi(e); if (v <= 0) Lc = 1 << 30; else { Lc = v; O = v / 2; } }  // diagnostics
+      if (n <= 640 || Lc + 2 * O > 640 || Lc >= n) { g.SL = (int)n; g.Lc = (int)n; g.O = 0; g.nseg = 1; }
+      else { g.Lc = Lc; g.O = O; g.SL = Lc + 2 * O; g.nseg = (int)((n + Lc - 1) / Lc); }
+      g.K = 0; while ((1 << g.K) < g.SL) ++g.K;
+      return g;
+    };
+    L.sy = make_seg(L.ny); L.sx = make_seg(L.nx);
     if (L.npx > 0) {
+      ARG_CHECK(ctx, L.sy.SL <= 1024 && L.sy.K <= 10 || L.sy.nseg > 1, "PML lines longer than 640 points need the segmented relaxation");
       CUDA_TRY(ctx, L.rxs.alloc((size_t)2 * L.npx * L.ny));
-      CUDA_TRY(ctx, L.pcr_y.alloc((size_t)2 * L.npx * (2 * L.Ky + 1) * L.ny));
-      scratch_need = std::max(scratch_need, (size_t)2 * L.npx * 6 * L.ny);
-      if ((size_t)2 * L.ny * sizeof(cplx<T>) > 200 * 1024) line_scratch_need = std::max(line_scratch_need, (size_t)2 * L.npx * 2 * L.ny);
+      CUDA_TRY(ctx, L.pcr_y.alloc((size_t)2 * L.npx * L.sy.nseg * (2 * L.sy.K + 1) * L.sy.SL));
+      scratch_need = std::max(scratch_need, (size_t)2 * L.npx * L.sy.nseg * 6 * L.sy.SL);
     }
     if (L.ys.count() > 0) {
       CUDA_TRY(ctx, L.rys.alloc((size_t)L.ys.count() * L.nx));
-      CUDA_TRY(ctx, L.pcr_x.alloc((size_t)L.ys.count() * (2 * L.Kx + 1) * L.nx));
-      scratch_need = std::max(scratch_need, (size_t)L.ys.count() * 6 * L.nx);
-      if ((size_t)2 * L.nx * sizeof(cplx<T>) > 200 * 1024) line_scratch_need = std::max(line_scratch_need, (size_t)L.ys.count() * 2 * L.nx);
+      CUDA_TRY(ctx, L.pcr_x.alloc((size_t)L.ys.count() * L.sx.nseg * (2 * L.sx.K + 1) * L.sx.SL));
+      scratch_need = std::max(scratch_need, (size_t)L.ys.count() * L.sx.nseg * 6 * L.sx.SL);
     }
   }
   if (first_level == 0) CUDA_TRY(ctx, spare.alloc((size_t)g.Nx * g.Ny));
-  for (auto& L : lv) { const int64_t nmax = std::max(L.nx, L.ny); if ((size_t)2 * nmax * sizeof(cplx<T>) > 200 * 1024) line_scratch_need = std::max(line_scratch_need, (size_t)(2 * L.npx + L.ys.count()) * 2 * nmax); }
   CUDA_TRY(ctx, pcr_scratch.alloc(scratch_need));
-  if (line_scratch_need) CUDA_TRY(ctx, line_scratch.alloc(line_scratch_need));
   for (size_t l = 0; l < lv.size(); ++l) {
     MGLevel<T>& L = lv[l];
     if (L.npx > 0) {
-      if (te) k_pcr_setup<T, true><<<2 * L.npx, 256, 0, ctx->stream>>>(L.view(), 0, L.npx, L.ys, L.Ky, pcr_scratch.p, L.pcr_y.p);
-      else k_pcr_setup<T, false><<<2 * L.npx, 256, 0, ctx->stream>>>(L.view(), 0, L.npx, L.ys, L.Ky, pcr_scratch.p, L.pcr_y.p);
+      if (te) k_pcr_setup<T, true><<<2 * L.npx * L.sy.nseg, 256, 0, ctx->stream>>>(L.view(), 0, L.npx, L.ys, L.sy, pcr_scratch.p, L.pcr_y.p);
+      else k_pcr_setup<T, false><<<2 * L.npx * L.sy.nseg, 256, 0, ctx->stream>>>(L.view(), 0, L.npx, L.ys, L.sy, pcr_scratch.p, L.pcr_y.p);
       KLAUNCH(ctx);
     }
     if (L.ys.count() > 0) {
-      if (te) k_pcr_setup<T, true><<<L.ys.count(), 256, 0, ctx->stream>>>(L.view(), 1, L.npy, L.ys, L.Kx, pcr_scratch.p, L.pcr_x.p);
-      else k_pcr_setup<T, false><<<L.ys.count(), 256, 0, ctx->stream>>>(L.view(), 1, L.npy, L.ys, L.Kx, pcr_scratch.p, L.pcr_x.p);
+      if (te) k_pcr_setup<T, true><<<L.ys.count() * L.sx.nseg, 256, 0, ctx->stream>>>(L.view(), 1, L.npy, L.ys, L.sx, pcr_scratch.p, L.pcr_x.p);
+      else k_pcr_setup<T, false><<<L.ys.count() * L.sx.nseg, 256, 0, ctx->stream>>>(L.view(), 1, L.npy, L.ys, L.sx, pcr_scratch.p, L.pcr_x.p);
       KLAUNCH(ctx);
     }
     CUDA_TRY(ctx, cudaGetLastError());
   }
-  // opt in to large dynamic shared memory for the line kernel
-  CUDA_TRY(ctx, cudaFuncSetAttribute(k_lines<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  CUDA_TRY(ctx, cudaFuncSetAttribute(k_lines2<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   pcr_scratch.release();
   return FDFD_OK;
 }
 
-template <typename T> int Multigrid<T>::smooth_classic(int l, bool zero) {
-  MGLevel<T>& L = lv[l];
-  const OpView<T> op = L.view();
-  dim3 grid((unsigned)((L.nx + kMgThreads - 1) / kMgThreads), (unsigned)((L.ny + kMgRows - 1) / kMgRows));
-  const T wj = T(prm.wjac), wl = T(prm.wline);
-  cplx<T>* out = zero ? L.u.p : L.tmp.p;
-#define SMOOTH(TEV, ZV) k_smooth_pt<T, TEV, ZV><<<grid, kMgThreads, 0, ctx->stream>>>(op, L.u.p, L.f.p, out, L.rxs.p, L.npx, L.npy, wj, done)
-  if (te) { if (zero) SMOOTH(true, true); else SMOOTH(true, false); }
-  else    { if (zero) SMOOTH(false, true); else SMOOTH(false, false); }
-#undef SMOOTH
-  KLAUNCH(ctx);
-  if (!zero) { std::swap(L.u.p, L.tmp.p); }  // u now holds the updated iterate
-  auto launch_lines = [&](int mode) {
-    const int64_t n = mode == 0 ? L.ny : L.nx;
-    const int np = mode == 0 ? L.npx : L.npy;
-    const int K = mode == 0 ? L.Ky : L.Kx;
-    const size_t smem = (size_t)2 * n * sizeof(cplx<T>);
-    const bool use_g = smem > 200 * 1024;
-    const int threads = (int)std::min<int64_t>(1024, std::max<int64_t>(32, ((n + 31) / 32) * 32));
-    k_lines<T><<<2 * np, threads, use_g ? 0 : smem, ctx->stream>>>(n, K, mode == 0 ? L.pcr_y.p : L.pcr_x.p,
-                                                                  mode == 0 ? L.rxs.p : L.rys.p, L.u.p, mode, L.nx, L.ny, np, wl,
-                                                                  use_g ? line_scratch.p : nullptr, done);
-    KLAUNCH(ctx);
-  };
-  if (L.npx > 0) launch_lines(0);
-  if (L.npy > 0) {
-    dim3 g2((unsigned)((L.nx + 127) / 128), (unsigned)(2 * L.npy));
-    if (te) k_resid_rows<T, true><<<g2, 128, 0, ctx->stream>>>(op, L.u.p, L.f.p, L.rys.p, L.npy, done);
-    else k_resid_rows<T, false><<<g2, 128, 0, ctx->stream>>>(op, L.u.p, L.f.p, L.rys.p, L.npy, done);
-    KLAUNCH(ctx);
-    launch_lines(1);
-  }
-  CUDA_TRY(ctx, cudaGetLastError());
-  return FDFD_OK;
-}
+// timing diagnostics only (results are wrong): FDFD_MG_SKIP bit 0 = no line relaxation, bit 1 = no tiled smoother,
+// bit 2 = no restriction, bit 3 = no zero-guess smoother
+static int mg_skip() { static const int v = []() { const char* e = getenv("FDFD_MG_SKIP"); return e ? atoi(e) : 0; }(); return v; }
 
 template <typename T> int Multigrid<T>::smooth(int l, bool zero, bool prolong) {
-  static const bool classic = []() { const char* e = getenv("FDFD_MG_SMOOTHER"); return e && atoi(e) == 4; }();
   MGLevel<T>& L = lv[l];
-  if (classic) {
-    if (prolong) {
-      MGLevel<T>& C = lv[l + 1];
-      dim3 grid((unsigned)((L.nx + 127) / 128), (unsigned)L.ny);
-      k_prolong_add<T><<<grid, 128, 0, ctx->stream>>>(L.nx, L.ny, C.nx, C.ny, L.pw.p, L.pw.p + 2 * L.nx, C.u.p, L.u.p, done);
-      KLAUNCH(ctx);
-    }
-    return smooth_classic(l, zero);
-  }
   const OpView<T> op = L.view();
   dim3 grid((unsigned)((L.nx + kMgThreads - 1) / kMgThreads), (unsigned)((L.ny + kMgRows - 1) / kMgRows));
   const T wj = T(prm.wjac), wl = T(prm.wline);
@@ -1045,20 +905,19 @@ template <typename T> int Multigrid<T>::smooth(int l, bool zero, bool prolong) {
 #define SM2(TEV, ZV, PV) k_smooth2<T, TEV, ZV, PV><<<grid, kMgThreads, 0, ctx->stream>>>(op, L.u.p, L.f.p, out, L.rxs.p, L.rys.p, L.npx, L.ys, wj, pv, done)
 #define SMT(TEV, PV) do { if (use_tile) k_smooth2_tile<T, TEV, PV><<<tgrid, kTileThreads, 0, ctx->stream>>>(op, L.u.p, L.f.p, out, L.rxs.p, L.rys.p, L.npx, L.ys, wj, pv, done); \
     else k_smooth2_march<T, TEV, PV><<<mgrid, 32 * kMWarps, 0, ctx->stream>>>(op, L.u.p, L.f.p, out, L.rxs.p, L.rys.p, L.npx, L.ys, wj, pv, done); } while (0)
-  if (te) { if (zero) SM2(true, true, false); else if (prolong) SMT(true, true); else SMT(true, false); }
+  if ((zero && (mg_skip() & 8)) || (!zero && (mg_skip() & 2))) {}
+  else if (te) { if (zero) SM2(true, true, false); else if (prolong) SMT(true, true); else SMT(true, false); }
   else    { if (zero) SM2(false, true, false); else if (prolong) SMT(false, true); else SMT(false, false); }
 #undef SM2
 #undef SMT
   KLAUNCH(ctx);
   if (!zero) std::swap(L.u.p, L.tmp.p);
-  const int nlines = 2 * L.npx + L.ys.count();
-  if (nlines > 0) {
-    const int64_t nmax = std::max(L.nx, L.ny);
-    const size_t smem = (size_t)2 * nmax * sizeof(cplx<T>);
-    const bool use_g = smem > 200 * 1024;
-    const int threads = (int)std::min<int64_t>(1024, std::max<int64_t>(32, ((nmax + 31) / 32) * 32));
-    k_lines2<T><<<nlines, threads, use_g ? 0 : smem, ctx->stream>>>(L.nx, L.ny, L.npx, L.ys, L.Ky, L.Kx, L.pcr_y.p, L.pcr_x.p,
-                                                                   L.rxs.p, L.rys.p, L.u.p, wl, use_g ? line_scratch.p : nullptr, done);
+  const int nblocks = 2 * L.npx * L.sy.nseg + L.ys.count() * L.sx.nseg;
+  if (nblocks > 0 && !(mg_skip() & 1)) {
+    const int slmax = std::max(L.npx > 0 ? L.sy.SL : 0, L.ys.count() > 0 ? L.sx.SL : 0);
+    const int threads = std::max(32, ((slmax + 31) / 32) * 32);
+    k_lines2<T><<<nblocks, threads, (size_t)2 * slmax * sizeof(cplx<T>), ctx->stream>>>(L.nx, L.ny, L.npx, L.ys, L.sy, L.sx, L.pcr_y.p, L.pcr_x.p,
+                                                                                     L.rxs.p, L.rys.p, L.u.p, wl, done);
     KLAUNCH(ctx);
   }
   CUDA_TRY(ctx, cudaGetLastError());
@@ -1070,6 +929,7 @@ template <typename T> int Multigrid<T>::restrict_residual(int l) {
   MGLevel<T>& C = lv[l + 1];
   {
     static const bool use_tile = []() { const char* e = getenv("FDFD_MG_KERNELS"); return !(e && std::string(e) == "march"); }();
+    if (mg_skip() & 4) return FDFD_OK;
     if (use_tile) {
       dim3 grid((unsigned)((C.nx + kCX - 1) / kCX), (unsigned)((C.ny + kCY - 1) / kCY));
       if (te) k_restrict_tile<T, true><<<grid, kTileThreads, 0, ctx->stream>>>(L.view(), L.u.p, L.f.p, C.nx, C.ny, L.rw.p, L.rw.p + 3 * C.nx, C.f.p, done);

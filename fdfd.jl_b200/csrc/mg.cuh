@@ -19,6 +19,20 @@
 #pragma once
 #include "device_ops.cuh"
 
+// A PML line (a strip column along y or a strip row along x) is relaxed in overlapping segments: segment j solves the
+// tridiagonal system of line points [j Lc - O, (j+1) Lc + O) (couplings cut at its ends) and updates its core
+// [j Lc, (j+1) Lc).  Inside the strips the line operator is diagonally dominant (|rho| <= ~0.95 per cell in the deepest
+// PML cells at level 0, far smaller elsewhere), so a cut O >= 128 cells away changes the core by < 1e-2 of a smoothing
+// update, while one 4096-point line becomes 16 independent 512-point systems: 1024 CTAs instead of 64 and 9 PCR steps
+// instead of 12 (measured: 67 us -> see DESIGN.md).  Lines of <= 640 points are a single exact segment.
+struct LineSeg {
+  int n = 0, SL = 0, Lc = 0, O = 0, nseg = 1, K = 0;   // line length, stored segment length, core, overlap, segments, PCR steps
+  __host__ __device__ int lo(int j) const { const int a = j * Lc - O; return a < 0 ? 0 : a; }
+  __host__ __device__ int hi(int j) const { const int b = (j + 1) * Lc + O; return b > n ? n : b; }
+  __host__ __device__ int core_lo(int j) const { return j * Lc; }
+  __host__ __device__ int core_hi(int j) const { const int b = (j + 1) * Lc; return (b > n || j == nseg - 1) ? n : b; }
+};
+
 // rows of the y-direction PML strip as two ranges [a0,a1) U [b0,b1)
 struct YS { int a0 = 0, a1 = 0, b0 = 0, b1 = 0; int count() const { return (a1 - a0) + (b1 - b0); } };
 
@@ -26,12 +40,12 @@ template <typename T> struct MGLevel {
   int64_t nx = 0, ny = 0, stride = 1;
   YS ys;                      // y-strip rows of this level (single GPU: [0,npy) U [ny-npy,ny))
   int npx = 0, npy = 0;       // strip half-widths: columns [0,npx) U [nx-npx,nx), rows likewise
-  int Kx = 0, Ky = 0;         // PCR steps of x-lines (length nx) / y-lines (length ny)
+  LineSeg sx, sy;             // segmentation of the x-lines (length nx) / y-lines (length ny)
   DevBuf<cplx<T>> c1d, mass, gx, gy;
   DevBuf<c128> eps;           // level eps_r (fp64), level 0 aliases the fine operator's copy (not owned)
   DevBuf<cplx<T>> u, f, tmp;
   DevBuf<cplx<T>> rxs, rys;   // strip residual buffers: [line][i]
-  DevBuf<cplx<T>> pcr_y, pcr_x;  // per line: alpha[K][n] | gamma[K][n] | binv[n]
+  DevBuf<cplx<T>> pcr_y, pcr_x;  // per (line, segment): alpha[K][SL] | gamma[K][SL] | binv[SL]
   DevBuf<cplx<T>> pw;         // prolongation weights of THIS level's points: wlx[nx] | wrx[nx] | wly[ny] | wry[ny]
   DevBuf<cplx<T>> rw;         // restriction weights to the next coarser level: RX[3*ncx] | RY[3*ncy]
   DevBuf<c128> rwd;           // same in fp64 (eps restriction at setup)
@@ -60,7 +74,6 @@ template <typename T> struct Multigrid {
   MGParams prm;
   std::vector<MGLevel<T>> lv;
   DevBuf<c128> pcr_scratch;   // setup-only scratch
-  DevBuf<cplx<T>> line_scratch;  // global ping-pong for lines too long for shared memory
   DevBuf<cplx<T>> spare;         // third level-0 buffer: lets the caller keep one result across the next apply
   double rhs_scale = 1.0;        // M is stored scaled by this factor (keeps fp32 in range); callers scale the rhs they write
   const int* done = nullptr;     // optional device flag: kernels early-exit once the Krylov loop has converged
@@ -78,6 +91,5 @@ template <typename T> struct Multigrid {
   // building blocks (public: the slab driver runs them in lock step over several slabs with halo exchanges between)
   int cycle(int l, bool zero, int kind);
   int smooth(int l, bool zero, bool prolong = false);
-  int smooth_classic(int l, bool zero);
   int restrict_residual(int l);
 };
