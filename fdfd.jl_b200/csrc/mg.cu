@@ -299,6 +299,186 @@ k_smooth2_tile(OpView<T> op, const cplx<T>* __restrict__ u, const cplx<T>* __res
   }
 }
 
+// ---- k_smooth3: column-marching smoother for the bandwidth-bound levels --------------------------------------------
+// One thread per fine column, kS3R rows per CTA (like the fp64 stencil).  Everything that depends on the column only
+// (x-parity, coarse column, x-interpolation weights, x coefficients) is computed once per thread; the row parity is static
+// because a CTA starts on an even row, so the coarse-grid correction costs one x-interpolation per coarse row and one
+// y-interpolation per odd fine row instead of a 2-D index decode + 4 loads per staged point (the 64x16 tile version spent
+// ~130 instructions per point and was issue bound at 3.2 TB/s).  The y-neighbours of the corrected iterate stay in
+// registers, the x-neighbours go through one shared-memory row per fine row, all global loads are issued before the
+// single barrier.  HBM traffic: u 8 + f 8 + mass 8 + out 8 B per point (+ 2 B coarse).
+constexpr int kS3T = 128;
+
+// a / b for the Jacobi update: fp32 uses the hardware reciprocal approximation (2 ulp; it only damps a smoothing update)
+__device__ __forceinline__ cplx<float> cdiv_fast(cplx<float> a, cplx<float> b) {
+  const float d = __fdividef(1.0f, b.x * b.x + b.y * b.y);
+  return cplx<float>((a.x * b.x + a.y * b.y) * d, (a.y * b.x - a.x * b.y) * d);
+}
+__device__ __forceinline__ cplx<double> cdiv_fast(cplx<double> a, cplx<double> b) { return cdiv(a, b); }
+
+// interior CTA of the TM smoother: no periodic wrap, no partial rows / columns, no PML strip in its rows or columns.
+// Straight-line code on constant row strides (the general path below spends > 2/3 of its instructions on index
+// arithmetic, bounds and strip predicates).
+template <typename T, bool PROLONG, int kS3R>
+__device__ __forceinline__ void smooth3_interior(const OpView<T>& op, const cplx<T>* __restrict__ u, const cplx<T>* __restrict__ f,
+                                                 cplx<T>* __restrict__ out, T wj, const ProlongView<T>& pv,
+                                                 cplx<T> (*sv)[kS3T + 2], int x0, int y0) {
+  const int nx = (int)op.nx, ny = (int)op.ny;
+  const int t = threadIdx.x, ix = x0 + t;
+  const size_t n0 = (size_t)y0 * nx + ix;
+  const cplx<T>* up = u + n0 - nx;          // row y0 - 1
+  const cplx<T>* fp = f + n0;
+  const cplx<T>* mp = op.mass + n0;
+  cplx<T> v[kS3R + 2], fr[kS3R], mr[kS3R];
+#pragma unroll
+  for (int q = 0; q < kS3R + 2; ++q) v[q] = up[(size_t)q * nx];
+#pragma unroll
+  for (int r = 0; r < kS3R; ++r) { fr[r] = fp[(size_t)r * nx]; mr[r] = mp[(size_t)r * nx]; }
+  if (PROLONG) {
+    const int nxc = (int)pv.nxc;
+    const int ox = ix & 1;
+    const cplx<T>* cp = pv.uc + (size_t)((y0 >> 1) - 1) * nxc + (ix >> 1);   // coarse row J0 - 1
+    // branch-free x-interpolation: even columns use weights (1, 0) and read the same coarse point twice
+    cplx<T> wxl(T(1), T(0)), wxr(T(0), T(0));
+    if (ox) { wxl = pv.pwx[ix]; wxr = pv.pwx[nx + ix]; }
+    cplx<T> cx[kS3R / 2 + 2];
+#pragma unroll
+    for (int j = 0; j < kS3R / 2 + 2; ++j) {
+      const cplx<T> c0 = cp[(size_t)j * nxc], c1 = cp[(size_t)j * nxc + ox];
+      cx[j] = ox ? wxl * c0 + wxr * c1 : c0;
+    }
+    const cplx<T>* wy = pv.pwy + (y0 - 1);
+#pragma unroll
+    for (int q = 0; q < kS3R + 2; ++q) {      // slot q <-> row y0 - 1 + q: odd rows are the even slots
+      if ((q & 1) == 0) v[q] += wy[q] * cx[q >> 1] + wy[ny + q] * cx[(q >> 1) + 1];
+      else v[q] += cx[(q + 1) >> 1];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < kS3R; ++r) sv[r][t + 1] = v[r + 1];
+  if (t < 2 * kS3R) {
+    const int side = t / kS3R, r = t - side * kS3R;
+    sv[r][side ? kS3T + 1 : 0] = iterate32<T, PROLONG>(u, pv, nx, ny, side ? x0 + kS3T : x0 - 1, y0 + r);
+  }
+  __syncthreads();
+  const cplx<T> W = op.cxm[ix], E = op.cxp[ix];
+  const cplx<T> mWE = -W - E;
+  cplx<T>* op_ = out + n0;
+#pragma unroll
+  for (int r = 0; r < kS3R; ++r) {
+    const cplx<T> S = op.cym[y0 + r], Nn = op.cyp[y0 + r];
+    const cplx<T> C = mr[r] - W - E - S - Nn;
+    const cplx<T> u0 = v[r + 1];
+    cplx<T> res = fr[r];
+    res -= C * u0; res -= W * sv[r][t]; res -= E * sv[r][t + 2]; res -= S * v[r]; res -= Nn * v[r + 2];
+    op_[(size_t)r * nx] = u0 + wj * cdiv_fast(res, C);
+  }
+  (void)mWE;
+}
+
+
+template <typename T, bool TE, bool PROLONG, int kS3R>
+__global__ void __launch_bounds__(kS3T, kS3R == 8 ? 4 : 6)
+k_smooth3(OpView<T> op, const cplx<T>* __restrict__ u, const cplx<T>* __restrict__ f, cplx<T>* __restrict__ out,
+          cplx<T>* __restrict__ rxs, cplx<T>* __restrict__ rys, int npx, YS ysr, T wj, ProlongView<T> pv,
+          const int* __restrict__ done) {
+  if (done && *done) return;
+  __shared__ cplx<T> sv[kS3R][kS3T + 2];
+  const int nx = (int)op.nx, ny = (int)op.ny;
+  const int x0 = blockIdx.x * kS3T, y0 = blockIdx.y * kS3R;
+  if (!TE) {
+    const bool interior = x0 >= 1 && x0 + kS3T + 1 <= nx && y0 >= 2 && y0 + kS3R + 2 <= ny &&
+                          x0 >= npx && x0 + kS3T <= nx - npx &&
+                          (y0 + kS3R <= ysr.a0 || y0 >= ysr.a1) && (y0 + kS3R <= ysr.b0 || y0 >= ysr.b1);
+    if (interior) { smooth3_interior<T, PROLONG, kS3R>(op, u, f, out, wj, pv, sv, x0, y0); return; }
+  }
+  const int t = threadIdx.x, ix = x0 + t;
+  const int ncols = min(kS3T, nx - x0);
+  const bool col = t < ncols;
+  cplx<T> v[kS3R + 2];   // own column: slot s <-> fine row y0 - 1 + s (periodic)
+  cplx<T> fr[kS3R], mr[kS3R];
+  if (col) {
+    // plain loads first (f, mass and the stored iterate of rows y0 .. y0 + R)
+#pragma unroll
+    for (int r = 0; r <= kS3R; ++r) {
+      const int iy = y0 + r;
+      if (iy < ny) {
+        const int n = ix + nx * iy;
+        v[r + 1] = u[n];
+        if (r < kS3R) { fr[r] = f[n]; mr[r] = TE ? op.mass_const : op.mass[n]; }
+      }
+    }
+    if (y0 > 0) v[0] = u[ix + nx * (y0 - 1)];
+    if (PROLONG) {
+      const int nxc = (int)pv.nxc, nyc = (int)pv.nyc;
+      const int I0 = ix >> 1;
+      const bool ox = ix & 1;
+      const int I1 = ox ? (I0 + 1 == nxc ? 0 : I0 + 1) : I0;
+      cplx<T> wxl(T(1), T(0)), wxr(T(0), T(0));
+      if (ox) { wxl = pv.pwx[ix]; wxr = pv.pwx[nx + ix]; }
+      const int J0 = y0 >> 1;
+      // x-interpolated coarse values of coarse rows J0 - 1 (slot 0) and J0 .. J0 + R/2 (slots 1..)
+      cplx<T> cx[kS3R / 2 + 2];
+#pragma unroll
+      for (int j = 0; j < kS3R / 2 + 2; ++j) {
+        int J = J0 - 1 + j;
+        if (J < 0) J = 0;          // unused (the row below row 0 takes the dynamic path)
+        J %= nyc;
+        const cplx<T>* rw = pv.uc + nxc * J;
+        cplx<T> c = rw[I0];
+        if (ox) c = wxl * c + wxr * rw[I1];
+        cx[j] = c;
+      }
+#pragma unroll
+      for (int r = 0; r <= kS3R; ++r) {      // row y0 + r has the parity of r
+        const int iy = y0 + r;
+        if (iy < ny) {
+          if (r & 1) v[r + 1] += pv.pwy[iy] * cx[(r >> 1) + 1] + pv.pwy[ny + iy] * cx[(r >> 1) + 2];
+          else v[r + 1] += cx[(r >> 1) + 1];
+        }
+      }
+      if (y0 > 0) v[0] += pv.pwy[y0 - 1] * cx[0] + pv.pwy[ny + y0 - 1] * cx[1];   // odd row 2 (J0 - 1) + 1
+    }
+    // periodic neighbours of the first / last row: any parity, generic path
+    if (y0 == 0) v[0] = iterate32<T, PROLONG>(u, pv, nx, ny, ix, ny - 1);
+#pragma unroll
+    for (int r = 1; r <= kS3R; ++r) if (y0 + r == ny) v[r + 1] = iterate32<T, PROLONG>(u, pv, nx, ny, ix, 0);
+#pragma unroll
+    for (int r = 0; r < kS3R; ++r) sv[r][t + 1] = v[r + 1];
+  }
+  if (t < 2 * kS3R) {   // the two columns next to the CTA's columns
+    const int side = t / kS3R, r = t - side * kS3R, iy = y0 + r;
+    if (iy < ny) {
+      const int gx = side ? (x0 + ncols == nx ? 0 : x0 + ncols) : (x0 == 0 ? nx - 1 : x0 - 1);
+      sv[r][side ? ncols + 1 : 0] = iterate32<T, PROLONG>(u, pv, nx, ny, gx, iy);
+    }
+  }
+  __syncthreads();
+  if (!col) return;
+  const bool xs = in_strip(ix, nx, npx);
+  const int ixp = ix + 1 == nx ? 0 : ix + 1;
+  const cplx<T> cW = op.cxm[ix], cE = op.cxp[ix];
+#pragma unroll
+  for (int r = 0; r < kS3R; ++r) {
+    const int iy = y0 + r;
+    if (iy >= ny) break;
+    const int n = ix + nx * iy;
+    const bool ys = ys_in(ysr, iy);
+    cplx<T> W = cW, E = cE, S = op.cym[iy], Nn = op.cyp[iy];
+    if (TE) {
+      const int iyp = iy + 1 == ny ? 0 : iy + 1;
+      W = W * op.gx[n]; E = E * op.gx[ixp + nx * iy]; S = S * op.gy[n]; Nn = Nn * op.gy[ix + nx * iyp];
+    }
+    const cplx<T> C = mr[r] - W - E - S - Nn;
+    const cplx<T> u0 = v[r + 1];
+    cplx<T> res = fr[r];
+    res -= C * u0; res -= W * sv[r][t]; res -= E * sv[r][t + 2]; res -= S * v[r]; res -= Nn * v[r + 2];
+    if (xs) rxs[(int)strip_line(ix, nx, npx) * ny + iy] = res;
+    if (ys) rys[(int)ys_line(ysr, iy) * nx + ix] = res;
+    out[n] = (xs || ys) ? u0 : u0 + wj * cdiv(res, C);
+  }
+}
+
 // k_restrict_tile: residual of a (2 CX + 1) x (2 CY + 1) fine patch computed once into shared memory, then the
 // CX x CY coarse points of the tile take their 3 x 3 weighted sums.  HBM traffic: u 8 + f 8 + mass 8 B per fine
 // point + 2 B write (fp32) instead of 2.25x recomputation with stride-2 access.
@@ -900,10 +1080,15 @@ template <typename T> int Multigrid<T>::smooth(int l, bool zero, bool prolong) {
   ProlongView<T> pv{0, 0, nullptr, nullptr, nullptr};
   if (prolong) { MGLevel<T>& C = lv[l + 1]; pv = ProlongView<T>{C.nx, C.ny, L.pw.p, L.pw.p + 2 * L.nx, C.u.p}; }
   static const bool use_tile = []() { const char* e = getenv("FDFD_MG_KERNELS"); return !(e && std::string(e) == "march"); }();
+  static const bool use_col = []() { const char* e = getenv("FDFD_MG_KERNELS"); return !e || std::string(e) == "col"; }();
+  static const int s3r = []() { const char* e = getenv("FDFD_MG_S3R"); return e && atoi(e) == 4 ? 4 : 8; }();
+  dim3 cgrid((unsigned)((L.nx + kS3T - 1) / kS3T), (unsigned)((L.ny + s3r - 1) / s3r));
   dim3 tgrid((unsigned)((L.nx + kTX - 1) / kTX), (unsigned)((L.ny + kTY - 1) / kTY));
   dim3 mgrid((unsigned)((L.nx + kMW * kMWarps - 1) / (kMW * kMWarps)), (unsigned)((L.ny + kMRows - 1) / kMRows));
 #define SM2(TEV, ZV, PV) k_smooth2<T, TEV, ZV, PV><<<grid, kMgThreads, 0, ctx->stream>>>(op, L.u.p, L.f.p, out, L.rxs.p, L.rys.p, L.npx, L.ys, wj, pv, done)
-#define SMT(TEV, PV) do { if (use_tile) k_smooth2_tile<T, TEV, PV><<<tgrid, kTileThreads, 0, ctx->stream>>>(op, L.u.p, L.f.p, out, L.rxs.p, L.rys.p, L.npx, L.ys, wj, pv, done); \
+#define SMT(TEV, PV) do { if (use_col && s3r == 8) k_smooth3<T, TEV, PV, 8><<<cgrid, kS3T, 0, ctx->stream>>>(op, L.u.p, L.f.p, out, L.rxs.p, L.rys.p, L.npx, L.ys, wj, pv, done); \
+    else if (use_col) k_smooth3<T, TEV, PV, 4><<<cgrid, kS3T, 0, ctx->stream>>>(op, L.u.p, L.f.p, out, L.rxs.p, L.rys.p, L.npx, L.ys, wj, pv, done); \
+    else if (use_tile) k_smooth2_tile<T, TEV, PV><<<tgrid, kTileThreads, 0, ctx->stream>>>(op, L.u.p, L.f.p, out, L.rxs.p, L.rys.p, L.npx, L.ys, wj, pv, done); \
     else k_smooth2_march<T, TEV, PV><<<mgrid, 32 * kMWarps, 0, ctx->stream>>>(op, L.u.p, L.f.p, out, L.rxs.p, L.rys.p, L.npx, L.ys, wj, pv, done); } while (0)
   if ((zero && (mg_skip() & 8)) || (!zero && (mg_skip() & 2))) {}
   else if (te) { if (zero) SM2(true, true, false); else if (prolong) SMT(true, true); else SMT(true, false); }
