@@ -485,6 +485,12 @@ class Problem:
         check(lib().fdfd_problem_bench_apply(self._h, nrep, C.byref(ms)), self.ctx.handle)
         return ms.value
 
+    def bench_mg(self, kind, nrep=50):
+        """ms per launch of one level-0 multigrid kernel (0 smoother+correction, 1 restriction, 2 zero-guess sweep, 4 cycle)"""
+        ms = C.c_double()
+        check(lib().fdfd_problem_bench_mg(self._h, int(kind), nrep, C.byref(ms)), self.ctx.handle)
+        return ms.value
+
     def flux_x(self, center, width, forward_h=False):
         """flux_surface_integral(field, center, width, x̂) (src/flux.jl:37-47) evaluated on the device from the resident Ez"""
         center = _pt(center)

@@ -60,7 +60,7 @@ EXPORTS = [
     "fdfd_default_opts", "fdfd_sfactors", "fdfd_assemble_derivative", "fdfd_assemble_system",
     "fdfd_apply_operator", "fdfd_solve_driven", "fdfd_solve_modulated", "fdfd_eigenfrequency",
     "fdfd_problem_create", "fdfd_problem_destroy", "fdfd_problem_set_rhs", "fdfd_problem_set_source",
-    "fdfd_problem_solve", "fdfd_problem_get_solution", "fdfd_problem_get_fields", "fdfd_problem_bench_apply",
+    "fdfd_problem_solve", "fdfd_problem_get_solution", "fdfd_problem_get_fields", "fdfd_problem_bench_apply", "fdfd_problem_bench_mg",
     "fdfd_problem_precond", "fdfd_problem_get_history", "fdfd_debug_hess_eig",
     "fdfd_problem_flux_x", "fdfd_rasterize",
     "fdfd_comm_unique_id", "fdfd_comm_create_nccl", "fdfd_comm_group_create", "fdfd_comm_group_destroy",
@@ -105,6 +105,7 @@ def lib():
         L.fdfd_problem_get_solution.argtypes = [vp, vp]
         L.fdfd_problem_get_fields.argtypes = [vp, i32, vp]
         L.fdfd_problem_bench_apply.argtypes = [vp, i32, C.POINTER(dbl)]
+        L.fdfd_problem_bench_mg.argtypes = [vp, i32, i32, C.POINTER(dbl)]
         L.fdfd_problem_precond.argtypes = [vp, vp, vp]
         L.fdfd_problem_get_history.argtypes = [vp, vp, i32, C.POINTER(i32)]
         L.fdfd_debug_hess_eig.argtypes = [i32, vp, vp, vp]

@@ -177,6 +177,47 @@ extern "C" int fdfd_problem_bench_apply(fdfd_problem* P, int nrep, double* ms_pe
   return FDFD_OK;
 }
 
+extern "C" int fdfd_problem_bench_mg(fdfd_problem* P, int kind, int nrep, double* ms_per_launch) {
+  if (!P) return FDFD_ERR_ARG;
+  fdfd_ctx* ctx = P->ctx;
+  ARG_CHECK(ctx, nrep > 0 && ms_per_launch, "bad arguments");
+  ARG_CHECK(ctx, P->mgf != nullptr && P->mgf->levels() >= 2, "needs the fp32 multigrid with at least two levels");
+  Multigrid<float>* mg = P->mgf;
+  const int64_t N = P->op.g.Nx * P->op.g.Ny;
+  const int* saved = mg->done; mg->done = nullptr;
+  // a realistic state: random right-hand side, one full cycle so that every level holds an iterate
+  k_fill_random<<<P->w.nvec_blocks, 256, 0, ctx->stream>>>(N, P->w.t.p, 4321); KLAUNCH(ctx);
+  k_cast_in<float><<<P->w.nvec_blocks, 256, 0, ctx->stream>>>(N, P->w.t.p, mg->rhs(), 1.0); KLAUNCH(ctx);
+  const c64* res = nullptr;
+  int st = mg->apply(&res);
+  auto one = [&]() -> int {
+    switch (kind) {
+      case 0: return mg->smooth(0, false, true);
+      case 1: return mg->restrict_residual(0);
+      case 2: return mg->smooth(0, true, false);
+      default: return mg->apply(&res);
+    }
+  };
+  for (int w = 0; w < 3 && st == FDFD_OK; ++w) st = one();
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (st == FDFD_OK && (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess)) st = FDFD_ERR_CUDA;
+  float ms = 0;
+  if (st == FDFD_OK) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaEventRecord(e0, ctx->stream);
+    for (int i = 0; i < nrep && st == FDFD_OK; ++i) st = one();
+    cudaEventRecord(e1, ctx->stream);
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms, e0, e1);
+  }
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  mg->done = saved;
+  FDFD_TRY(st);
+  *ms_per_launch = (double)ms / nrep;
+  return FDFD_OK;
+}
+
 extern "C" int fdfd_problem_get_history(fdfd_problem* P, double* out, int n, int* written) {
   if (!P) return FDFD_ERR_ARG;
   fdfd_ctx* ctx = P->ctx;

@@ -177,6 +177,10 @@ int fdfd_problem_get_solution(fdfd_problem* p, fdfd_c128* x);             /* (Nx
 int fdfd_problem_get_fields(fdfd_problem* p, int forward_h, fdfd_c128* fields); /* (Nx,Ny,3) */
 /* timed loop of nrep matrix-free applies on resident data; ms_per_apply from CUDA events */
 int fdfd_problem_bench_apply(fdfd_problem* p, int nrep, double* ms_per_apply);
+/* timed loop of one multigrid kernel on the level-0 arrays of the resident hierarchy (fp32 multigrid only).  kind: 0 = smoothing
+ * sweep fused with the coarse-grid correction (k_smooth3 + the PML line kernel), 1 = residual + restriction
+ * (k_restrict_tile), 2 = zero-guess sweep (k_smooth2 + the PML line kernel), 4 = one whole cycle (M^-1 applied once). */
+int fdfd_problem_bench_mg(fdfd_problem* p, int kind, int nrep, double* ms_per_launch);
 /* relative residual history of the last solve: out[k] = ||r_k|| / ||b|| (recurrence residual), k = 0..n-1;
  * returns the number of entries written through *written */
 int fdfd_problem_get_history(fdfd_problem* p, double* out, int n, int* written);
