@@ -74,8 +74,8 @@ extern "C" void fdfd_default_opts(fdfd_solve_opts_t* o) {
   o->mg_nu1 = 1; o->mg_nu2 = 1;
   o->mg_coarse_sweeps = 2;
   o->mg_beta = 0.5;
-  o->mg_wjac = 0.8;
-  o->mg_wline = 0.7;
+  o->mg_wjac = 0.7;
+  o->mg_wline = 0.6;
   o->check_every = 8;
   o->verbose = 0;
   o->mg_shift_growth = 0.0;

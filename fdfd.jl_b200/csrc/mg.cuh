@@ -61,7 +61,7 @@ template <typename T> struct MGLevel {
 
 struct MGParams {
   int cycle = FDFD_CYCLE_W, wdepth = 4, nu1 = 1, nu2 = 1, coarse_sweeps = 4;
-  double beta = 0.5, wjac = 0.8, wline = 0.7, shift_growth = 0.0;
+  double beta = 0.5, wjac = 0.7, wline = 0.6, shift_growth = 0.0;
   int min_n = 2, pad = 1, max_levels = 32;
   double kh_stop = 4.0;
 };

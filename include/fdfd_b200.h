@@ -79,8 +79,8 @@ typedef struct {
   int32_t mg_nu1, mg_nu2;/* pre/post smoothing sweeps (default 1,1) */
   int32_t mg_coarse_sweeps; /* sweeps on the coarsest level (default 2) */
   double  mg_beta;       /* complex shift: M = L + (1 - i*beta) w^2 eps (default 0.5) */
-  double  mg_wjac;       /* point-Jacobi damping (default 0.8) */
-  double  mg_wline;      /* PML line-relaxation damping (default 0.7) */
+  double  mg_wjac;       /* point-Jacobi damping (default 0.7; measured on the 4096^2 sweep: 0.8 needs 15 % more iterations, 0.9 twice as many) */
+  double  mg_wline;      /* PML line-relaxation damping (default 0.6) */
   int32_t check_every;   /* host polls convergence every k iterations (default 8) */
   int32_t verbose;
   double  mg_shift_growth; /* level/space dependent shift: beta_eff = max(beta, growth * Re(k^2 h_l^2)) (default 0 = off) */
