@@ -65,6 +65,7 @@ EXPORTS = [
     "fdfd_problem_flux_x", "fdfd_rasterize",
     "fdfd_comm_unique_id", "fdfd_comm_create_nccl", "fdfd_comm_group_create", "fdfd_comm_group_destroy",
     "fdfd_comm_create_threads", "fdfd_comm_destroy", "fdfd_slab_rows", "fdfd_solve_driven_slab", "fdfd_comm_stats",
+    "fdfd_solve_modulated_slab", "fdfd_eigenfrequency_slab",
 ]
 COMM_THREADS, COMM_NCCL = 0, 1
 COMM_ID_BYTES = 128
@@ -121,6 +122,8 @@ def lib():
         L.fdfd_comm_destroy.restype = None
         L.fdfd_slab_rows.argtypes = [G, i32, i32, C.POINTER(i64), C.POINTER(i64)]
         L.fdfd_solve_driven_slab.argtypes = [vp, vp, G, dbl, vp, vp, C.POINTER(SolveOpts), vp, C.POINTER(Info)]
+        L.fdfd_solve_modulated_slab.argtypes = [vp, vp, G, dbl, dbl, i32, i32, vp, vp, vp, C.POINTER(SolveOpts), vp, C.POINTER(Info)]
+        L.fdfd_eigenfrequency_slab.argtypes = [vp, vp, G, i32, dbl, i32, i32, i32, vp, C.POINTER(SolveOpts), vp, vp, C.POINTER(Info)]
         L.fdfd_comm_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
         _lib = L
     return _lib

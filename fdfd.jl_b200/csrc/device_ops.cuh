@@ -42,7 +42,7 @@ struct FineOp {
             double omega_pml = 0.0);
   // slab of the global grid gg: eps_local_any holds the (nyl + 2H) x Nx local rows (halo rows included, periodic wrap)
   int build_slab(fdfd_ctx* ctx, const fdfd_grid_t& gg, int ordering, double omega, const fdfd_c128* eps_local_any,
-                 int64_t y0, int64_t nyl, int nlevels, int64_t halo);
+                 int64_t y0, int64_t nyl, int nlevels, int64_t halo, double omega_pml = 0.0);
   OpView<double> view() const {
     OpView<double> v;
     v.nx = g.Nx; v.ny = g.Ny;

@@ -63,7 +63,10 @@ __global__ void k_seed(int64_t N, c128* __restrict__ x, uint64_t seed) {
   }
 }
 
+}  // namespace
+
 // ---- host: eigen-decomposition of a small complex upper-Hessenberg matrix (column major, ld = n) -----------
+// (external linkage: shared with slab_multi.cu)
 // shifted QR with Givens rotations -> Schur form T = Z^H H Z, then eigenvectors of T by back substitution.
 bool hess_eig(int n, std::vector<cd> H, std::vector<cd>& evals, std::vector<cd>& evecs) {
   auto at = [&](std::vector<cd>& M, int i, int j) -> cd& { return M[(size_t)j * n + i]; };
@@ -154,8 +157,6 @@ double which_key(int which, cd nu) {
     default: return std::abs(nu);
   }
 }
-
-}  // namespace
 
 extern "C" int fdfd_eigenfrequency(fdfd_ctx* ctx, const fdfd_grid_t* g, int pol, double omega0, int nev, int which, int ncv,
                                    const fdfd_c128* eps_r, const fdfd_solve_opts_t* opts, fdfd_c128* omega_out,

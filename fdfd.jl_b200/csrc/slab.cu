@@ -162,7 +162,9 @@ struct SlabSolver {
   }
 };
 
-// depth of the slab hierarchy (levels 0..L-1 on the slab's rows) and the agglomeration level ka (-1: none)
+}  // namespace
+
+// depth of the slab hierarchy (levels 0..L-1 on the slab's rows) and the agglomeration level ka (-1: none); also used by slab_multi.cu
 void slab_depth(const fdfd_grid_t& g, double omega, const MGParams& prm, int64_t nyl, int* nlev_out, int* ka_out) {
   const std::vector<std::pair<int64_t, int64_t>> sizes = mg_level_sizes(g, omega, prm, 0);
   auto fits = [&](int L) { const int64_t h = (int64_t)1 << (L - 1); return nyl % h == 0 && g.Ny % h == 0 && h <= nyl; };
@@ -181,6 +183,8 @@ void slab_depth(const fdfd_grid_t& g, double omega, const MGParams& prm, int64_t
   while (L > 1 && !fits(L)) --L;
   *nlev_out = L; *ka_out = -1;
 }
+
+namespace {
 
 int solve_slab(fdfd_ctx* ctx, fdfd_comm* comm, const fdfd_grid_t* g, double omega, const fdfd_c128* eps_rows,
                const fdfd_c128* src_rows, const fdfd_solve_opts_t* opts, fdfd_c128* fields_rows, fdfd_info_t* info) {

@@ -185,8 +185,8 @@ static int apply_variant() {
 static int variant_rows(int v) { static const int rows[8] = {4, 8, 16, 4, 8, 16, 32, 8}; return rows[v]; }
 
 int FineOp::build_slab(fdfd_ctx* ctx, const fdfd_grid_t& gg, int ordering_, double omega_, const fdfd_c128* eps_local_any,
-                       int64_t y0, int64_t nyl, int nlevels, int64_t halo) {
-  pol = FDFD_TM; ordering = ordering_; omega = omega_; omega_pml = omega_;
+                       int64_t y0, int64_t nyl, int nlevels, int64_t halo, double omega_pml_) {
+  pol = FDFD_TM; ordering = ordering_; omega = omega_; omega_pml = omega_pml_ > 0 ? omega_pml_ : omega_;
   slab.on = true; slab.gg = gg; slab.y0 = y0; slab.nyl = nyl; slab.nlevels = nlevels; slab.H = halo;
   ARG_CHECK(ctx, halo >= 1 && halo % ((int64_t)1 << (nlevels - 1)) == 0 && halo <= nyl, "slab halo must be a multiple of 2^(levels-1) and at most the slab height");
   ARG_CHECK(ctx, nyl % ((int64_t)1 << (nlevels - 1)) == 0 && y0 % ((int64_t)1 << (nlevels - 1)) == 0 && gg.Ny % ((int64_t)1 << (nlevels - 1)) == 0,

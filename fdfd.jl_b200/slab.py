@@ -159,6 +159,115 @@ def solve_slabs_threads(d, nslabs: int, devices=None, **kw):
     return FieldTM(d.grid, d.omega[0], data, infos[0]), infos
 
 
+def _run_threads(nslabs, devices, work):
+    """one host thread (own context and stream) per slab; re-raises the first error"""
+    comms = SlabComm.threads(nslabs)
+    devices = devices or [0] * nslabs
+    ctxs = [Context(dev) for dev in devices]
+    errs = [None] * nslabs
+
+    def run(r):
+        try:
+            work(r, comms[r], ctxs[r])
+        except Exception as e:  # noqa: BLE001 - reported below
+            errs[r] = e
+
+    th = [threading.Thread(target=run, args=(r,)) for r in range(nslabs)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for c in comms:
+        c.close()
+    for c in ctxs:
+        c.close()
+    for e in errs:
+        if e is not None:
+            raise e
+
+
+# ---- slab-sharded modulated / eigenfrequency solves (csrc/slab_multi.cu; written without GPU access, see its header) ----
+def solve_modulated_slab_rows(grid, omega, Omega, nsidebands, sharedpml, eps_rows, deps_rows, src_rows, comm: SlabComm,
+                              ctx: Context, **kw):
+    """This rank's rows of solve(d::ModulatedDevice) (modulation.jl:35-119): returns fields (Nx, nrows, 3, nf), sideband
+    -ns first, and the solve info.  Collective over `comm`."""
+    o = kw.pop("opts", None) or default_opts(**kw)
+    Nx, _ = grid.N
+    _, n = slab_rows(grid, comm.nranks, comm.rank)
+    nf = 2 * int(nsidebands) + 1
+    eps_rows = _lib.as_c128(eps_rows, (Nx, n)); deps_rows = _lib.as_c128(deps_rows, (Nx, n)); src_rows = _lib.as_c128(src_rows, (Nx, n))
+    fields = np.empty((Nx, n, 3, nf), dtype=np.complex128, order="F")
+    info = Info()
+    gc = grid.as_c()
+    code = lib().fdfd_solve_modulated_slab(ctx.handle, comm.handle, C.byref(gc), float(omega), float(Omega), int(nsidebands),
+                                           int(bool(sharedpml)), ptr(eps_rows), ptr(deps_rows), ptr(src_rows), C.byref(o),
+                                           ptr(fields), C.byref(info))
+    check(code, ctx.handle)
+    return fields, info.asdict()
+
+
+def solve_modulated_slabs_threads(d, nslabs: int, devices=None, **kw):
+    """solve(d::ModulatedDevice) with the grid cut into `nslabs` row slabs, all from one process (tests).  Returns
+    ([FieldTM per sideband], [info per slab]); single frequency."""
+    from . import FieldTM
+    if len(d.omega) != 1:
+        raise ValueError("the slab modulated solve takes a single frequency")
+    Nx, Ny = d.grid.N
+    nf = 2 * d.nsidebands + 1
+    data = np.empty((Nx, Ny, 3, nf), dtype=np.complex128, order="F")
+    infos = [None] * nslabs
+
+    def work(r, comm, ctx):
+        y0, n = slab_rows(d.grid, nslabs, r)
+        f, info = solve_modulated_slab_rows(d.grid, d.omega[0], d.Omega, d.nsidebands, d.sharedpml, d.eps_r[:, y0:y0 + n],
+                                            d.deps_r[:, y0:y0 + n], d.src[:, y0:y0 + n], comm, ctx, **dict(kw))
+        data[:, y0:y0 + n, :, :] = f
+        infos[r] = info
+
+    _run_threads(nslabs, devices, work)
+    omegan = d.omega[0] + d.Omega * np.arange(-d.nsidebands, d.nsidebands + 1)
+    return [FieldTM(d.grid, omegan[j], data[:, :, :, j], infos[0]) for j in range(nf)], infos
+
+
+def eigenfrequency_slab_rows(grid, omega0, nev, eps_rows, comm: SlabComm, ctx: Context, which="LM", ncv=0, want_fields=True, **kw):
+    """This rank's rows of eigenfrequency(d, TM, nev; which) (eigen.jl:69-96): (ω[nev], fields (Nx, nrows, 3, nev) or None,
+    info).  Collective over `comm`; ω is identical on every rank."""
+    o = kw.pop("opts", None) or default_opts(**kw)
+    Nx, _ = grid.N
+    _, n = slab_rows(grid, comm.nranks, comm.rank)
+    eps_rows = _lib.as_c128(eps_rows, (Nx, n))
+    om = np.empty(nev, dtype=np.complex128)
+    fields = np.empty((Nx, n, 3, nev), dtype=np.complex128, order="F") if want_fields else None
+    info = Info()
+    gc = grid.as_c()
+    code = lib().fdfd_eigenfrequency_slab(ctx.handle, comm.handle, C.byref(gc), _lib.TM, float(omega0), int(nev),
+                                          _lib.WHICH[which], int(ncv), ptr(eps_rows), C.byref(o), ptr(om), ptr(fields),
+                                          C.byref(info))
+    check(code, ctx.handle)
+    return om, fields, info.asdict()
+
+
+def eigenfrequency_slabs_threads(d, nev, nslabs: int, which="LM", ncv=0, devices=None, **kw):
+    """eigenfrequency(d, TM, nev) with the grid cut into `nslabs` row slabs, all from one process (tests).
+    Returns (ω, [FieldTM], [info per slab])."""
+    from . import FieldTM
+    Nx, Ny = d.grid.N
+    data = np.empty((Nx, Ny, 3, nev), dtype=np.complex128, order="F")
+    oms, infos = [None] * nslabs, [None] * nslabs
+
+    def work(r, comm, ctx):
+        y0, n = slab_rows(d.grid, nslabs, r)
+        om, f, info = eigenfrequency_slab_rows(d.grid, d.omega[0], nev, d.eps_r[:, y0:y0 + n], comm, ctx, which=which, ncv=ncv, **dict(kw))
+        data[:, y0:y0 + n, :, :] = f
+        oms[r], infos[r] = om, info
+
+    _run_threads(nslabs, devices, work)
+    for om in oms[1:]:
+        if not np.array_equal(om, oms[0]):
+            raise RuntimeError("slab eigenfrequencies differ between ranks")
+    return oms[0], [FieldTM(d.grid, oms[0][i], data[:, :, :, i], infos[0]) for i in range(nev)], infos
+
+
 def gather_field(grid, omega, rows_data, rank, world, info=None, group=None):
     """Assemble the full FieldTM on rank 0 from every rank's (Nx, nrows, 3) rows (torch.distributed gather; any backend).
     Other ranks get None.  Only for grids whose (Nx,Ny,3) field fits one host; large runs keep the rows sharded."""

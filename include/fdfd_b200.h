@@ -229,6 +229,24 @@ int fdfd_slab_rows(const fdfd_grid_t* g, int nranks, int rank, int64_t* y0, int6
 int fdfd_solve_driven_slab(fdfd_ctx* ctx, fdfd_comm* comm, const fdfd_grid_t* g, double omega,
                            const fdfd_c128* eps_r_rows, const fdfd_c128* src_rows, const fdfd_solve_opts_t* opts,
                            fdfd_c128* fields_rows, fdfd_info_t* info);
+/* ---- slab-sharded modulated and eigenfrequency solves (csrc/slab_multi.cu).
+ * STATUS: written without GPU access, compiled only; exercised by tests/unverified (FDFD_RUN_UNVERIFIED=1) until they have
+ * run on hardware.  Same slab layout, communicators and collective-call rules as fdfd_solve_driven_slab.
+ *
+ * solve(d::ModulatedDevice) (src/solver/modulation.jl:35-119) on row slabs: the sideband coupling is pointwise
+ * (modulation.jl:95-98), so all nf = 2*nsidebands+1 sidebands of a row live on the rank that owns the row and the
+ * coupling needs no exchange.  eps_r_rows, deps_r_rows, src_rows: (Nx, nrows); fields_rows: nf x (Nx, nrows, 3),
+ * sideband -ns first, H from forward differences (modulation.jl:112-113). */
+int fdfd_solve_modulated_slab(fdfd_ctx* ctx, fdfd_comm* comm, const fdfd_grid_t* g, double omega, double Omega,
+                              int nsidebands, int sharedpml, const fdfd_c128* eps_r_rows, const fdfd_c128* deps_r_rows,
+                              const fdfd_c128* src_rows, const fdfd_solve_opts_t* opts, fdfd_c128* fields_rows,
+                              fdfd_info_t* info);
+/* eigenfrequency(d, TM, nev; which) (src/solver/eigen.jl:69-96) on row slabs: the Arnoldi basis is sharded like every
+ * other vector, the inner shift-invert solves are slab solves, the Hessenberg matrix is replicated on the hosts.
+ * pol must be FDFD_TM.  omega_out: nev complex (identical on every rank); fields_rows: nev x (Nx, nrows, 3) or NULL. */
+int fdfd_eigenfrequency_slab(fdfd_ctx* ctx, fdfd_comm* comm, const fdfd_grid_t* g, int pol, double omega0, int nev,
+                             int which, int ncv, const fdfd_c128* eps_r_rows, const fdfd_solve_opts_t* opts,
+                             fdfd_c128* omega_out, fdfd_c128* fields_rows, fdfd_info_t* info);
 /* counters of the communicator since creation: exchanges, allreduces, bytes sent by this rank */
 int fdfd_comm_stats(fdfd_comm* comm, int64_t* n_exchange, int64_t* n_allreduce, int64_t* bytes_sent);
 
