@@ -137,4 +137,28 @@ function solve_slab_b200(d::Device{2}, comm::Ptr{Cvoid}, nranks::Int, rank::Int)
     return out
 end
 
+"solve(d::ModulatedDevice) of one frequency on row slabs (csrc/slab_multi.cu); returns this rank's (Nx, nrows, 3, nf) rows"
+function solve_slab_b200(d::ModulatedDevice{2}, comm::Ptr{Cvoid}, nranks::Int, rank::Int)
+    rows = slab_rows(d.grid, nranks, rank); (Nx, _) = size(d.grid); nf = 2 * d.nsidebands + 1
+    ϵ = ComplexF64.(d.ϵᵣ[:, rows]); Δϵ = ComplexF64.(d.Δϵᵣ[:, rows]); src = ComplexF64.(d.src[:, rows])
+    out = Array{ComplexF64}(undef, Nx, length(rows), 3, nf); opts = COpts(); info = CInfo()
+    GC.@preserve ϵ Δϵ src out check(ccall((:fdfd_solve_modulated_slab, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ref{CGrid}, Float64, Float64, Cint, Cint, Ptr{ComplexF64}, Ptr{ComplexF64}, Ptr{ComplexF64},
+         Ref{COpts}, Ptr{ComplexF64}, Ref{CInfo}),
+        ctx(), comm, CGrid(d.grid), d.ω[1], d.Ω, d.nsidebands, d.sharedpml, ϵ, Δϵ, src, opts, out, info))
+    return out
+end
+
+"eigenfrequency(d, TM, nev; which) on row slabs; returns (ω, this rank's (Nx, nrows, 3, nev) rows of the mode fields)"
+function eigenfrequency_slab_b200(d::AbstractDevice{2}, nev::Int, comm::Ptr{Cvoid}, nranks::Int, rank::Int; which::Symbol=:LM)
+    rows = slab_rows(d.grid, nranks, rank); (Nx, _) = size(d.grid)
+    ϵ = ComplexF64.(d.ϵᵣ[:, rows]); ω = Array{ComplexF64}(undef, nev); out = Array{ComplexF64}(undef, Nx, length(rows), 3, nev)
+    opts = COpts(); info = CInfo()
+    GC.@preserve ϵ ω out check(ccall((:fdfd_eigenfrequency_slab, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ref{CGrid}, Cint, Float64, Cint, Cint, Cint, Ptr{ComplexF64}, Ref{COpts}, Ptr{ComplexF64},
+         Ptr{ComplexF64}, Ref{CInfo}),
+        ctx(), comm, CGrid(d.grid), Int32(TM), d.ω[1], nev, WHICH[which], 0, ϵ, opts, ω, out, info))
+    return (ω, out)
+end
+
 end # module
