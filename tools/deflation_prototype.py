@@ -63,7 +63,7 @@ def fgmres(A, b, prec, tol, maxit, m=60):
     return x, total
 
 
-def inexact_study(n):
+def inexact_study(n, inners=(None, 40, 20, 10, 5)):
     A, b, lu = problem(n); Minv = lu.solve; nb = np.linalg.norm(b)
     P1 = prolong1d(n); Z = sp.kron(P1, P1, format="csr")
     E = (Z.T @ A @ Z).tocsc()
@@ -77,7 +77,7 @@ def inexact_study(n):
     Mc = spla.splu((Z.T @ Mf @ Z).tocsc())
     Elu = spla.splu(E)
     print(f"n={n}: outer FGMRES iterations with the level-1 coarse system solved by `inner` BiCGSTAB steps (exact coarse CSL inverse)")
-    for inner in (None, 40, 20, 10, 5):
+    for inner in inners:
         cnt = [0]
         def coarse(g):
             if inner is None: return Elu.solve(g)
@@ -90,4 +90,4 @@ def inexact_study(n):
 
 
 if __name__ == "__main__" and len(sys.argv) > 2 and sys.argv[2] == "inexact":
-    inexact_study(int(sys.argv[1]))
+    inexact_study(int(sys.argv[1]), tuple(None if a == 'exact' else int(a) for a in sys.argv[3:]) or (None, 40, 20, 10, 5))
