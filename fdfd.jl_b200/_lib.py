@@ -14,7 +14,7 @@ TM, TE = 1, 2
 ORDER_FB, ORDER_BF = 0, 1
 DXF, DXB, DYF, DYB = 0, 1, 2, 3
 CSR, CSC = 0, 1
-SOLVER_BICGSTAB, SOLVER_COCG = 0, 1
+SOLVER_BICGSTAB, SOLVER_COCG, SOLVER_MLKRYLOV = 0, 1, 2
 PRECOND_NONE, PRECOND_JACOBI, PRECOND_MG = 0, 1, 2
 MG_F32, MG_F64 = 0, 1
 CYCLE_V, CYCLE_F, CYCLE_W = 0, 1, 2
@@ -34,7 +34,7 @@ class SolveOpts(C.Structure):
                 ("mg_beta", C.c_double), ("mg_wjac", C.c_double), ("mg_wline", C.c_double),
                 ("check_every", C.c_int32), ("verbose", C.c_int32),
                 ("mg_shift_growth", C.c_double), ("mg_max_levels", C.c_int32), ("use_graph", C.c_int32),
-                ("concurrency", C.c_int32), ("reserved", C.c_int32)]
+                ("concurrency", C.c_int32), ("ml_spec", C.c_int32)]
 
 
 class Info(C.Structure):
@@ -65,7 +65,8 @@ EXPORTS = [
     "fdfd_problem_flux_x", "fdfd_rasterize",
     "fdfd_comm_unique_id", "fdfd_comm_create_nccl", "fdfd_comm_group_create", "fdfd_comm_group_destroy",
     "fdfd_comm_create_threads", "fdfd_comm_destroy", "fdfd_slab_rows", "fdfd_solve_driven_slab", "fdfd_comm_stats",
-    "fdfd_solve_modulated_slab", "fdfd_eigenfrequency_slab",
+    "fdfd_solve_modulated_slab", "fdfd_eigenfrequency_slab", "fdfd_problem_ml_cycles",
+    "fdfd_debug_ml_lsq", "fdfd_debug_ml_transfer",
 ]
 COMM_THREADS, COMM_NCCL = 0, 1
 COMM_ID_BYTES = 128
@@ -108,6 +109,9 @@ def lib():
         L.fdfd_problem_bench_apply.argtypes = [vp, i32, C.POINTER(dbl)]
         L.fdfd_problem_bench_mg.argtypes = [vp, i32, i32, C.POINTER(dbl)]
         L.fdfd_problem_precond.argtypes = [vp, vp, vp]
+        L.fdfd_problem_ml_cycles.argtypes = [vp, C.POINTER(i64)]
+        L.fdfd_debug_ml_lsq.argtypes = [i32, vp, dbl, vp, C.POINTER(dbl)]
+        L.fdfd_debug_ml_transfer.argtypes = [i64, i64, i32, dbl, vp, vp]
         L.fdfd_problem_get_history.argtypes = [vp, vp, i32, C.POINTER(i32)]
         L.fdfd_debug_hess_eig.argtypes = [i32, vp, vp, vp]
         L.fdfd_problem_flux_x.argtypes = [vp, dbl, dbl, dbl, i32, C.POINTER(dbl)]

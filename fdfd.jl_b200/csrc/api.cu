@@ -61,7 +61,8 @@ extern "C" int fdfd_problem_create(fdfd_ctx* ctx, const fdfd_grid_t* g, int pol,
   fdfd_problem* P = new fdfd_problem();
   P->ctx = ctx;
   if (opts) P->opts = *opts; else fdfd_default_opts(&P->opts);
-  if (!(P->opts.solver == FDFD_SOLVER_BICGSTAB || P->opts.solver == FDFD_SOLVER_COCG)) { delete P; fdfd_set_error(ctx, "fdfd_problem_create: solver must be FDFD_SOLVER_BICGSTAB or FDFD_SOLVER_COCG"); return FDFD_ERR_ARG; }
+  if (!(P->opts.solver == FDFD_SOLVER_BICGSTAB || P->opts.solver == FDFD_SOLVER_COCG || P->opts.solver == FDFD_SOLVER_MLKRYLOV)) { delete P; fdfd_set_error(ctx, "fdfd_problem_create: solver must be FDFD_SOLVER_BICGSTAB, FDFD_SOLVER_COCG or FDFD_SOLVER_MLKRYLOV"); return FDFD_ERR_ARG; }
+  if (P->opts.solver == FDFD_SOLVER_MLKRYLOV && !(pol == FDFD_TM && P->opts.precond == FDFD_PRECOND_MG && P->opts.mg_precision == FDFD_MG_F32)) { delete P; fdfd_set_error(ctx, "fdfd_problem_create: FDFD_SOLVER_MLKRYLOV needs TM, FDFD_PRECOND_MG and FDFD_MG_F32"); return FDFD_ERR_ARG; }
   if (P->opts.solver == FDFD_SOLVER_COCG && P->opts.precond == FDFD_PRECOND_MG) { delete P; fdfd_set_error(ctx, "fdfd_problem_create: COCG needs a symmetric preconditioner (FDFD_PRECOND_JACOBI or FDFD_PRECOND_NONE); the multigrid cycle is not symmetric"); return FDFD_ERR_ARG; }
   const double t0 = now_ms();
   int st = P->op.build(ctx, *g, pol, ordering, omega, eps_r);
@@ -122,6 +123,7 @@ extern "C" int fdfd_problem_solve(fdfd_problem* P, fdfd_info_t* info) {
   CUDA_TRY(P->ctx, cudaSetDevice(P->ctx->device));
   const double t0 = now_ms();
   if (P->opts.solver == FDFD_SOLVER_COCG) { FDFD_TRY(krylov_cocg(P, info)); }
+  else if (P->opts.solver == FDFD_SOLVER_MLKRYLOV) { FDFD_TRY(krylov_multilevel(P, info)); }
   else { KrylovOps ops = P->make_ops(); FDFD_TRY(krylov_bicgstab(P->ctx, P->w, ops, P->opts, info)); }
   info->setup_ms = P->setup_ms;
   info->mg_levels = P->mgf ? P->mgf->levels() : (P->mgd ? P->mgd->levels() : 0);

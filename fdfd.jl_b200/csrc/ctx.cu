@@ -82,7 +82,7 @@ extern "C" void fdfd_default_opts(fdfd_solve_opts_t* o) {
   o->mg_max_levels = 32;
   o->use_graph = 1;
   o->concurrency = 4;
-  o->reserved = 0;
+  o->ml_spec = 0;
 }
 
 static bool is_device_ptr(const void* p) {

@@ -204,7 +204,7 @@ KrylovWork::~KrylovWork() {
   if (h_scal) cudaFreeHost(h_scal);
 }
 
-fdfd_problem::~fdfd_problem() { delete mgf; delete mgd; }
+fdfd_problem::~fdfd_problem() { mlkrylov_free(ml); delete mgf; delete mgd; }
 
 int jacobi_apply(fdfd_ctx* ctx, const FineOp& op, const c128* in, c128* out, const int* done, int blocks) {
   // KScal::done sits at a fixed offset; the kernel takes the KScal pointer

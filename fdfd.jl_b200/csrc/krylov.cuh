@@ -51,6 +51,9 @@ int krylov_bicgstab(fdfd_ctx* ctx, KrylovWork& W, const KrylovOps& ops, const fd
 int vec_blocks_for(fdfd_ctx* ctx, int64_t n);
 int apply_num_blocks(int64_t nx, int64_t ny);
 
+struct MLKrylov;
+void mlkrylov_free(MLKrylov* m);
+
 struct fdfd_problem {
   fdfd_ctx* ctx = nullptr;
   FineOp op;
@@ -60,10 +63,12 @@ struct fdfd_problem {
   KrylovWork w;
   double setup_ms = 0;
   bool have_rhs = false;
+  MLKrylov* ml = nullptr;   // state of the multilevel Krylov solver (FDFD_SOLVER_MLKRYLOV), built at the first solve
   KrylovOps make_ops();
   ~fdfd_problem();
 };
 
 MGParams mg_params_from(const fdfd_solve_opts_t& o);
 int krylov_cocg(fdfd_problem* P, fdfd_info_t* info);
+int krylov_multilevel(fdfd_problem* P, fdfd_info_t* info);
 int jacobi_apply(fdfd_ctx* ctx, const FineOp& op, const c128* in, c128* out, const int* done, int blocks);

@@ -945,6 +945,7 @@ template <typename T> int Multigrid<T>::setup(fdfd_ctx* ctx_, const FineOp& op, 
       hier_coefs(HY, (int)l, scale / (hy * hy), hc.cym, hc.cyp);
       hc.cym = ysl(hc.cym, (int)l, 1); hc.cyp = ysl(hc.cyp, (int)l, 1);
     }
+    L.hc = hc;
     {  // transfer weights: prolongation from level l+1 (fine-indexed wl|wr) and restriction to level l+1
       std::vector<cplx<T>> pw; pw.reserve(2 * L.nx + 2 * L.ny);
       const std::vector<cdh> wly = ysl(HY.wl[l], (int)l, 1), wry = ysl(HY.wr[l], (int)l, 1);

@@ -50,6 +50,7 @@ template <typename T> struct MGLevel {
   DevBuf<cplx<T>> rw;         // restriction weights to the next coarser level: RX[3*ncx] | RY[3*ncy]
   DevBuf<c128> rwd;           // same in fp64 (eps restriction at setup)
   cplx<T> mass_const{T(0), T(0)};
+  Coef1D hc;                  // host copy of this level's 1-D coefficients in fp64, unscaled (multilevel Krylov builds A_l from it)
   OpView<T> view() const {
     OpView<T> v;
     v.nx = nx; v.ny = ny;

@@ -22,7 +22,7 @@ mutable struct COpts    # fdfd_solve_opts_t
     solver::Int32; precond::Int32; tol::Float64; maxit::Int32; mg_precision::Int32; mg_cycle::Int32
     mg_wdepth::Int32; mg_nu1::Int32; mg_nu2::Int32; mg_coarse_sweeps::Int32
     mg_beta::Float64; mg_wjac::Float64; mg_wline::Float64; check_every::Int32; verbose::Int32
-    mg_shift_growth::Float64; mg_max_levels::Int32; use_graph::Int32; concurrency::Int32; reserved::Int32
+    mg_shift_growth::Float64; mg_max_levels::Int32; use_graph::Int32; concurrency::Int32; ml_spec::Int32
     COpts() = (o = new(); ccall((:fdfd_default_opts, LIB), Cvoid, (Ref{COpts},), o); o)
 end
 

@@ -50,7 +50,10 @@ enum { FDFD_DXF = 0, FDFD_DXB = 1, FDFD_DYF = 2, FDFD_DYB = 3 };
 enum { FDFD_CSR = 0, FDFD_CSC = 1 };
 /* Krylov solvers / preconditioners */
 /* BICGSTAB: any preconditioner.  COCG: on the symmetrised system diag(sxf*syf) A, Jacobi or no preconditioner. */
-enum { FDFD_SOLVER_BICGSTAB = 0, FDFD_SOLVER_COCG = 1 };
+/* MLKRYLOV (opt-in; csrc/mlkrylov.cu, compiled but not yet run on a GPU): multilevel Krylov -- flexible GMRES on every level,
+ * preconditioned by the multigrid cycle plus a coarse-grid Helmholtz correction solved by the same method one level down.
+ * TM, FDFD_PRECOND_MG, FDFD_MG_F32 only. */
+enum { FDFD_SOLVER_BICGSTAB = 0, FDFD_SOLVER_COCG = 1, FDFD_SOLVER_MLKRYLOV = 2 };
 enum { FDFD_PRECOND_NONE = 0, FDFD_PRECOND_JACOBI = 1, FDFD_PRECOND_MG = 2 };
 enum { FDFD_MG_F32 = 0, FDFD_MG_F64 = 1 };
 enum { FDFD_CYCLE_V = 0, FDFD_CYCLE_F = 1, FDFD_CYCLE_W = 2 };
@@ -87,7 +90,8 @@ typedef struct {
   int32_t mg_max_levels; /* cap on hierarchy depth (default 32) */
   int32_t use_graph;     /* replay the iteration as a CUDA graph (default 1) */
   int32_t concurrency;   /* fdfd_solve_driven: frequencies solved concurrently on separate streams (default 4) */
-  int32_t reserved;
+  int32_t ml_spec;       /* FDFD_SOLVER_MLKRYLOV: k1 | k2<<8 | k3<<16 | restart<<24 = FGMRES steps per solve on levels 1,2,3 (0 ends the
+                            list) and the level-0 restart length; 0 = defaults (6, 12; restart 40) */
 } fdfd_solve_opts_t;
 
 typedef struct {
@@ -184,6 +188,8 @@ int fdfd_problem_bench_mg(fdfd_problem* p, int kind, int nrep, double* ms_per_la
 /* relative residual history of the last solve: out[k] = ||r_k|| / ||b|| (recurrence residual), k = 0..n-1;
  * returns the number of entries written through *written */
 int fdfd_problem_get_history(fdfd_problem* p, double* out, int n, int* written);
+/* multigrid cycles started on levels 0..3 by the last FDFD_SOLVER_MLKRYLOV solve (diagnostics) */
+int fdfd_problem_ml_cycles(fdfd_problem* p, int64_t* out4);
 /* one application of the preconditioner M^-1 to a resident vector (parity/debug hook) */
 int fdfd_problem_precond(fdfd_problem* p, const fdfd_c128* in, fdfd_c128* out);
 
@@ -253,6 +259,12 @@ int fdfd_comm_stats(fdfd_comm* comm, int64_t* n_exchange, int64_t* n_allreduce, 
 /* host-only test hook (no GPU needed): the small dense complex Hessenberg eigen-solver behind the Ritz pairs of
  * fdfd_eigenfrequency.  H, evecs: column-major n x n; evals: n. */
 int fdfd_debug_hess_eig(int n, const fdfd_c128* H, fdfd_c128* evals, fdfd_c128* evecs);
+
+/* host-only test hooks of FDFD_SOLVER_MLKRYLOV (no GPU needed): the one-thread least-squares solve of the (k+1) x k
+ * Hessenberg system min || beta e1 - H y || (H column-major, ld = k+1), and the grid transfers between a fine (nx,ny) grid
+ * and its vertex-centred coarse grid ((nx+1)/2, (ny+1)/2): mode 0 = scale * Z^T (fine -> coarse), mode 1 = Z (coarse -> fine). */
+int fdfd_debug_ml_lsq(int k, const fdfd_c128* H, double beta, fdfd_c128* y, double* resnorm);
+int fdfd_debug_ml_transfer(int64_t nx, int64_t ny, int mode, double scale, const fdfd_c128* in, fdfd_c128* out);
 
 #ifdef __cplusplus
 }

@@ -79,3 +79,52 @@ def test_hessenberg_eigensolver_host(fdfd):
         assert max(min(abs(e - ref)) for e in ev) < 1e-10 * max(1, abs(ref).max())
         for k in range(n):
             assert np.linalg.norm(H @ vec[:, k] - ev[k] * vec[:, k]) < 1e-10 * max(1, abs(ref).max())
+
+
+def test_mlkrylov_least_squares_core_host(fdfd):
+    """the one-thread Givens least-squares solve of the multilevel Krylov solver (csrc/mlkrylov.cu), run on the host"""
+    import numpy as np
+    from fdfd_jl_b200._lib import ptr
+    L = fdfd.lib()
+    rng = np.random.default_rng(3)
+    for k in (1, 2, 7, 40, 96):
+        H = np.zeros((k + 1, k), complex)
+        for j in range(k):
+            H[:j + 2, j] = rng.standard_normal(j + 2) + 1j * rng.standard_normal(j + 2)
+        Hf = np.asfortranarray(H)
+        y = np.zeros(k, complex)
+        res = ctypes.c_double()
+        assert L.fdfd_debug_ml_lsq(k, ptr(Hf), 1.75, ptr(y), ctypes.byref(res)) == 0
+        g = np.zeros(k + 1, complex)
+        g[0] = 1.75
+        yr = np.linalg.lstsq(H, g, rcond=None)[0]
+        assert np.abs(y - yr).max() <= 1e-13 * np.linalg.cond(H) * max(1.0, np.abs(yr).max())   # random Hessenberg matrices are ill-conditioned for large k
+        assert abs(np.linalg.norm(g - H @ y) - np.linalg.norm(g - H @ yr)) <= 1e-12
+        assert abs(res.value - np.linalg.norm(g - H @ yr)) <= 1e-12
+    # a zero column (lucky breakdown) must not produce NaNs
+    H = np.asfortranarray(np.zeros((3, 2), complex)); H[0, 0] = 2.0
+    y = np.zeros(2, complex)
+    assert L.fdfd_debug_ml_lsq(2, ptr(H), 1.0, ptr(y), None) == 0 and np.all(np.isfinite(y)) and abs(y[0] - 0.5) < 1e-15
+
+
+def test_mlkrylov_transfers_host(fdfd):
+    """Z (bilinear, coarse I <-> fine 2I, periodic) and Z^T of the multilevel Krylov solver are adjoint, Z reproduces
+    constants, and Z^T Z / 4 has unit row sums on even grids -- checked on the host for even, odd and mixed sizes"""
+    import numpy as np
+    from fdfd_jl_b200._lib import ptr
+    L = fdfd.lib()
+    rng = np.random.default_rng(4)
+    for nx, ny in ((8, 6), (9, 7), (8, 7), (5, 4), (64, 33)):
+        ncx, ncy = (nx + 1) // 2, (ny + 1) // 2
+        v = np.asfortranarray(rng.standard_normal((nx, ny)) + 1j * rng.standard_normal((nx, ny)))
+        y = np.asfortranarray(rng.standard_normal((ncx, ncy)) + 1j * rng.standard_normal((ncx, ncy)))
+        zt = np.zeros((ncx, ncy), complex, order="F")
+        z = np.zeros((nx, ny), complex, order="F")
+        assert L.fdfd_debug_ml_transfer(nx, ny, 0, 1.0, ptr(v), ptr(zt)) == 0
+        assert L.fdfd_debug_ml_transfer(nx, ny, 1, 1.0, ptr(y), ptr(z)) == 0
+        assert abs(np.vdot(z, v) - np.vdot(y, zt)) <= 1e-12 * np.linalg.norm(z) * np.linalg.norm(v)
+        one = np.asfortranarray(np.ones((ncx, ncy), complex))
+        assert L.fdfd_debug_ml_transfer(nx, ny, 1, 1.0, ptr(one), ptr(z)) == 0 and np.abs(z - 1).max() == 0
+        if nx % 2 == 0 and ny % 2 == 0:
+            ones_f = np.asfortranarray(np.ones((nx, ny), complex))
+            assert L.fdfd_debug_ml_transfer(nx, ny, 0, 0.25, ptr(ones_f), ptr(zt)) == 0 and np.abs(zt - 1).max() < 1e-15

@@ -1,0 +1,86 @@
+"""GPU tests of the multilevel Krylov solver (csrc/mlkrylov.cu, FDFD_SOLVER_MLKRYLOV).
+
+NOT part of `-m gpu`: written in a session without GPU access, compiled only (its arithmetic cores -- least-squares solve,
+grid transfers -- are checked on the CPU by tests/test_cabi_cpu.py).  Run with
+    FDFD_RUN_UNVERIFIED=1 python -m pytest tests/unverified -x -q --timeout 900
+on a B200; once green, move into tests/test_gpu_parity.py.  Bars are those of the default solver: true relative residual
+<= 1e-10 of the reference operator, fields within 1e-6 relative L2 of the oracle's direct solve."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = [pytest.mark.gpu_unverified,
+              pytest.mark.skipif(os.environ.get("FDFD_RUN_UNVERIFIED") != "1", reason="unverified GPU path: set FDFD_RUN_UNVERIFIED=1 on a GPU box")]
+
+W200 = 2 * math.pi * 200e12
+FIELD_TOL = 1e-6
+RES_TOL = 1e-10
+
+
+def rel(a, b):
+    return np.linalg.norm(np.ravel(a) - np.ravel(b)) / np.linalg.norm(np.ravel(b))
+
+
+def spec(k1, k2=0, k3=0, restart=0):
+    return k1 | (k2 << 8) | (k3 << 16) | (restart << 24)
+
+
+def waveguide(fdfd, Nx, Ny, npml=(15, 10), dh=0.02):
+    g = fdfd.Grid(dh, list(npml), [0.0, Nx * dh], [-Ny * dh / 2, Ny * dh / 2])
+    d = fdfd.Device(g, W200)
+    fdfd.setup_eps_r(d, lambda x, y: abs(y) <= 0.15, 12.0)
+    fdfd.setup_src(d, fdfd.Point(0.6, 0.0), fdfd.XHAT)
+    return d
+
+
+def oracle_fields(d):
+    from oracle import fdfd_oracle as O
+    g = d.grid
+    go = O.Grid2D(0.02, list(g.Npml), [g.bounds[0][0], g.bounds[1][0]], [g.bounds[0][1], g.bounds[1][1]])
+    do = O.Device(go, [d.omega[0]])
+    do.eps_r[:] = d.eps_r
+    do.src[:] = d.src
+    return O.solve(do, O.TM)["data"]
+
+
+@pytest.mark.parametrize("size", [(192, 128), (201, 101), (250, 100)])      # even, odd (the transfers' short last edge), mixed
+@pytest.mark.parametrize("ml_spec", [0, spec(8), spec(4, 6, 6)])          # defaults (6,12), two levels, four levels
+def test_mlkrylov_waveguide_vs_oracle(fdfd, size, ml_spec):
+    d = waveguide(fdfd, *size)
+    f = fdfd.solve(d, fdfd.TM, solver=fdfd._lib.SOLVER_MLKRYLOV, ml_spec=ml_spec)
+    assert f.info["flag"] == 0 and f.info["relres"] <= RES_TOL
+    assert rel(f.data, oracle_fields(d)) <= FIELD_TOL
+
+
+def test_mlkrylov_vs_default_solver_synthetic(fdfd):
+    """512^2 synthetic map (bench workload at reduced size): same field as BiCGSTAB + multigrid, fewer fine cycles"""
+    from fdfd_jl_b200 import workloads
+    d = workloads.synthetic_tm_device(fdfd, 512, 512, density=1.0 / 160.0)
+    ref = fdfd.solve(d, fdfd.TM)
+    f = fdfd.solve(d, fdfd.TM, solver=fdfd._lib.SOLVER_MLKRYLOV)
+    assert f.info["flag"] == 0 and f.info["relres"] <= RES_TOL
+    assert rel(f.data, ref.data) <= FIELD_TOL
+    # CPU prototype (tools/multilevel_prototype.py 512 300,6,-12): ~30 outer iterations vs ~93 BiCGSTAB iterations
+    assert f.info["iters"] <= ref.info["iters"]
+
+
+def test_mlkrylov_graph_and_plain_launches_agree(fdfd):
+    d = waveguide(fdfd, 256, 128)
+    a = fdfd.solve(d, fdfd.TM, solver=fdfd._lib.SOLVER_MLKRYLOV, use_graph=1)
+    b = fdfd.solve(d, fdfd.TM, solver=fdfd._lib.SOLVER_MLKRYLOV, use_graph=0)
+    assert a.info["flag"] == 0 and b.info["flag"] == 0
+    assert a.info["iters"] == b.info["iters"]
+    assert rel(a.data, b.data) <= 1e-12
+
+
+def test_mlkrylov_zero_source_and_bad_arguments(fdfd):
+    g = fdfd.Grid(0.02, [10, 10], [0.0, 2.56], [0.0, 2.56])
+    d = fdfd.Device(g, W200)
+    f = fdfd.solve(d, fdfd.TM, solver=fdfd._lib.SOLVER_MLKRYLOV)
+    assert f.info["flag"] == 0 and np.all(f.data == 0)
+    with pytest.raises(fdfd.FdfdError):
+        fdfd.solve(d, fdfd.TE, solver=fdfd._lib.SOLVER_MLKRYLOV)                    # TM only
+    with pytest.raises(fdfd.FdfdError):
+        fdfd.solve(d, fdfd.TM, solver=fdfd._lib.SOLVER_MLKRYLOV, mg_precision=1)     # fp32 multigrid only
