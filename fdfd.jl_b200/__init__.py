@@ -506,6 +506,12 @@ class Problem:
         check(lib().fdfd_problem_get_history(self._h, ptr(out), nmax, C.byref(n)), self.ctx.handle)
         return out[:n.value].copy()
 
+    def ml_cycles(self):
+        """multigrid cycles started on levels 0..3 by the last FDFD_SOLVER_MLKRYLOV solve"""
+        out = (C.c_int64 * 4)()
+        check(lib().fdfd_problem_ml_cycles(self._h, out), self.ctx.handle)
+        return list(out)
+
     def precond(self, v):
         vin = as_c128(v, self.grid.N)
         out = np.empty(self.grid.N, dtype=np.complex128, order="F")

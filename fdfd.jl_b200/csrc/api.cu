@@ -225,7 +225,7 @@ extern "C" int fdfd_problem_get_history(fdfd_problem* P, double* out, int n, int
   fdfd_ctx* ctx = P->ctx;
   ARG_CHECK(ctx, out && n > 0 && written, "bad arguments");
   const KScal h = *P->w.h_scal;
-  const int cnt = std::min(std::min(n, h.iter + 1), (int)P->w.hist.n);
+  const int cnt = std::max(0, std::min(std::min(n, h.iter + 1), (int)P->w.hist.n));
   std::vector<double> tmp(cnt);
   CUDA_TRY(ctx, cudaMemcpyAsync(tmp.data(), P->w.hist.p, cnt * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));

@@ -196,6 +196,7 @@ int KrylovWork::alloc(fdfd_ctx* ctx, int64_t n_, int nparts, int maxit, bool jac
   WALLOC(hist, (size_t)std::max(16, maxit + 2));
 #undef WALLOC
   if (cudaMallocHost((void**)&h_scal, sizeof(KScal)) != cudaSuccess) { fdfd_set_error(ctx, "cudaMallocHost failed"); return FDFD_ERR_ALLOC; }
+  std::memset(h_scal, 0, sizeof(KScal));   // readable (iter = 0) before the first BiCGSTAB solve and after solves by other methods
   return FDFD_OK;
 }
 

@@ -8,7 +8,7 @@ level down; the last level in `spec` runs BiCGSTAB + multigrid cycle only.
     python tools/multilevel_prototype.py N outer,k1[,k2...]      e.g.  1024 300,8,6
 Prints the number of multigrid cycles started on every level (what the GPU pays) and a bandwidth cost estimate.
 """
-import sys, time
+import os, sys, time
 import numpy as np, scipy.sparse as sp
 sys.path.insert(0, "/root/repo")
 from oracle import fdfd_oracle as O
@@ -50,6 +50,10 @@ def main():
     beta = float(sys.argv[3]) if len(sys.argv) > 3 else 0.5
     inner_tol = float(sys.argv[4]) if len(sys.argv) > 4 else 0.0
     d = synth_device(n, n)
+    if os.environ.get("BENCH_MAP"):   # the bench workload's map (density 1/160) instead of the prototype's denser one (1/40)
+        import fdfd_jl_b200 as fdfd
+        from fdfd_jl_b200 import workloads as wl
+        d.eps_r[:] = wl.synthetic_tm_device(fdfd, n, n, density=1 / 160).eps_r
     g = d.grid; omega = d.omega[0]
     eps0, mu0, _ = O.normalize_parameters(g)
     cxm, cxp, cym, cyp = O.stencil_coefficients(g, omega, "fb")

@@ -5,7 +5,7 @@ GMRES.  Counts what the GPU would pay: fine multigrid cycles, fine operator appl
 
     python tools/twolevel_prototype.py N [inner=5] [beta=0.5] [mode=adef1|mult]
 """
-import sys, time, math
+import os, sys, time, math
 import numpy as np, scipy.sparse as sp
 sys.path.insert(0, "/root/repo")
 from oracle import fdfd_oracle as O
@@ -58,6 +58,10 @@ def main():
     beta = float(sys.argv[3]) if len(sys.argv) > 3 else 0.5
     mode = sys.argv[4] if len(sys.argv) > 4 else "adef1"
     d = synth_device(n, n)
+    if os.environ.get("BENCH_MAP"):   # the bench workload's map (density 1/160) instead of the prototype's denser one (1/40)
+        import fdfd_jl_b200 as fdfd
+        from fdfd_jl_b200 import workloads as wl
+        d.eps_r[:] = wl.synthetic_tm_device(fdfd, n, n, density=1 / 160).eps_r
     g = d.grid; omega = d.omega[0]
     eps0, mu0, _ = O.normalize_parameters(g)
     cxm, cxp, cym, cyp = O.stencil_coefficients(g, omega, "fb")
