@@ -62,7 +62,7 @@ extern "C" int fdfd_problem_create(fdfd_ctx* ctx, const fdfd_grid_t* g, int pol,
   P->ctx = ctx;
   if (opts) P->opts = *opts; else fdfd_default_opts(&P->opts);
   if (!(P->opts.solver == FDFD_SOLVER_BICGSTAB || P->opts.solver == FDFD_SOLVER_COCG || P->opts.solver == FDFD_SOLVER_MLKRYLOV)) { delete P; fdfd_set_error(ctx, "fdfd_problem_create: solver must be FDFD_SOLVER_BICGSTAB, FDFD_SOLVER_COCG or FDFD_SOLVER_MLKRYLOV"); return FDFD_ERR_ARG; }
-  if (P->opts.solver == FDFD_SOLVER_MLKRYLOV && !(pol == FDFD_TM && P->opts.precond == FDFD_PRECOND_MG && P->opts.mg_precision == FDFD_MG_F32)) { delete P; fdfd_set_error(ctx, "fdfd_problem_create: FDFD_SOLVER_MLKRYLOV needs TM, FDFD_PRECOND_MG and FDFD_MG_F32"); return FDFD_ERR_ARG; }
+  if (P->opts.solver == FDFD_SOLVER_MLKRYLOV && !(P->opts.precond == FDFD_PRECOND_MG && P->opts.mg_precision == FDFD_MG_F32)) { delete P; fdfd_set_error(ctx, "fdfd_problem_create: FDFD_SOLVER_MLKRYLOV needs FDFD_PRECOND_MG and FDFD_MG_F32"); return FDFD_ERR_ARG; }
   if (P->opts.solver == FDFD_SOLVER_COCG && P->opts.precond == FDFD_PRECOND_MG) { delete P; fdfd_set_error(ctx, "fdfd_problem_create: COCG needs a symmetric preconditioner (FDFD_PRECOND_JACOBI or FDFD_PRECOND_NONE); the multigrid cycle is not symmetric"); return FDFD_ERR_ARG; }
   const double t0 = now_ms();
   int st = P->op.build(ctx, *g, pol, ordering, omega, eps_r);

@@ -43,9 +43,9 @@ struct FineOp {
   // slab of the global grid gg: eps_local_any holds the (nyl + 2H) x Nx local rows (halo rows included, periodic wrap)
   int build_slab(fdfd_ctx* ctx, const fdfd_grid_t& gg, int ordering, double omega, const fdfd_c128* eps_local_any,
                  int64_t y0, int64_t nyl, int nlevels, int64_t halo, double omega_pml = 0.0);
-  // rediscretised TM operator of a multigrid level (multilevel Krylov): 1-D coefficients hc_ (nx | ny entries, unscaled),
-  // mass = w^2 eps0 L0 eps_l with eps_l resident in HBM.  Only Nx, Ny of the grid member are meaningful afterwards.
-  int build_level(fdfd_ctx* ctx, const fdfd_grid_t& gfine, int64_t nx, int64_t ny, const Coef1D& hc_, double omega, const c128* eps_dev);
+  // rediscretised operator of a multigrid level (multilevel Krylov): 1-D coefficients hc_ (nx | ny entries, unscaled);
+  // TM: mass = w^2 eps0 L0 eps_l, TE: inverse averaged eps_l + the constant w^2 mu0 L0 term; eps_l resident in HBM.  Only Nx, Ny of the grid member are meaningful afterwards.
+  int build_level(fdfd_ctx* ctx, const fdfd_grid_t& gfine, int pol, int64_t nx, int64_t ny, const Coef1D& hc_, double omega, const c128* eps_dev);
   OpView<double> view() const {
     OpView<double> v;
     v.nx = g.Nx; v.ny = g.Ny;

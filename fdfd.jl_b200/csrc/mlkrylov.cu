@@ -244,7 +244,7 @@ int ml_setup(fdfd_problem* P, MLKrylov& M) {
     if (l == 0) L.op = &P->op;
     else {
       L.own.reset(new FineOp());
-      FDFD_TRY(L.own->build_level(ctx, P->op.g, L.nx, L.ny, mg->lv[l].hc, P->op.omega, mg->lv[l].eps.p));
+      FDFD_TRY(L.own->build_level(ctx, P->op.g, P->op.pol, L.nx, L.ny, mg->lv[l].hc, P->op.omega, mg->lv[l].eps.p));
       L.op = L.own.get();
       MALLOC(L.rhs, L.N); MALLOC(L.x, L.N);
     }
@@ -292,7 +292,7 @@ int ml_precond(MLKrylov& M, int li, const c128* v, c128* z) {
     FDFD_TRY(ml_solve_level(M, li + 1));
     k_ml_prolong<<<L.nb, 256, 0, st>>>(L.nx, L.ny, C.nx, C.ny, C.x.p, L.q.p); KLAUNCH(ctx);
     DotSpec d0;
-    FDFD_TRY(launch_apply(ctx, L.op->view(), false, L.q.p, false, L.t.p, d0));
+    FDFD_TRY(launch_apply(ctx, L.op->view(), L.op->pol == FDFD_TE, L.q.p, false, L.t.p, d0));
     q = L.q.p; t = L.t.p;
   }
   k_ml_to_mg<<<L.nb, 256, 0, st>>>(L.N, v, t, mg->lv[L.l].f.p, mg->rhs_scale); KLAUNCH(ctx);
@@ -310,7 +310,7 @@ int ml_arnoldi_step(MLKrylov& M, int li, int j) {
   MLLevel& L = *M.lev[li];
   FDFD_TRY(ml_precond(M, li, L.V[j].p, L.Z[j].p));
   DotSpec d0;
-  FDFD_TRY(launch_apply(ctx, L.op->view(), false, L.Z[j].p, false, L.w.p, d0));
+  FDFD_TRY(launch_apply(ctx, L.op->view(), L.op->pol == FDFD_TE, L.Z[j].p, false, L.w.p, d0));
   c128* Hj = L.H.p + (size_t)j * (L.k + 1);
   for (int i = 0; i <= j; ++i) {
     FDFD_TRY(ml_dot(ctx, L, L.V[i].p, L.w.p, Hj + i, 0));
@@ -389,7 +389,7 @@ int ml_solve_level(MLKrylov& M, int li) {
 // level 0: restarted flexible GMRES on the reference operator, true residual at every restart
 int krylov_multilevel(fdfd_problem* P, fdfd_info_t* info) {
   fdfd_ctx* ctx = P->ctx;
-  ARG_CHECK(ctx, P->mgf != nullptr && P->op.pol == FDFD_TM, "the multilevel Krylov solver needs the fp32 multigrid preconditioner and TM polarisation");
+  ARG_CHECK(ctx, P->mgf != nullptr, "the multilevel Krylov solver needs the fp32 multigrid preconditioner");
   ARG_CHECK(ctx, P->mgf->levels() >= 2, "the multilevel Krylov solver needs a multigrid hierarchy of at least 2 levels");
   if (!P->ml) {
     P->ml = new MLKrylov();
@@ -449,7 +449,7 @@ int krylov_multilevel(fdfd_problem* P, fdfd_info_t* info) {
       if (j > 0) { k_ml_combine<<<L.nb, 256, 0, st>>>(N, j, L.y.p, L.Zptr.p, x, 1); KLAUNCH(ctx); }
       // ---- true residual with the fp64 operator
       DotSpec d0;
-      FDFD_TRY(launch_apply(ctx, P->op.view(), false, x, false, t, d0));
+      FDFD_TRY(launch_apply(ctx, P->op.view(), P->op.pol == FDFD_TE, x, false, t, d0));
       k_ml_resid<<<L.nb, kT, 0, st>>>(N, b, t, r, L.parts.p); KLAUNCH(ctx);
       k_ml_dot_final<<<1, kT, 0, st>>>(L.parts.p, L.nb, L.sc.p + 3, 1); KLAUNCH(ctx);
       FDFD_TRY(fetch(L.sc.p + 3, 1));

@@ -221,23 +221,30 @@ int FineOp::build_slab(fdfd_ctx* ctx, const fdfd_grid_t& gg, int ordering_, doub
   return FDFD_OK;
 }
 
-int FineOp::build_level(fdfd_ctx* ctx, const fdfd_grid_t& gfine, int64_t nx, int64_t ny, const Coef1D& hc_, double omega_, const c128* eps_dev) {
+int FineOp::build_level(fdfd_ctx* ctx, const fdfd_grid_t& gfine, int pol_, int64_t nx, int64_t ny, const Coef1D& hc_, double omega_, const c128* eps_dev) {
   g = gfine; g.Nx = nx; g.Ny = ny;
-  pol = FDFD_TM; ordering = FDFD_ORDER_FB; omega = omega_; omega_pml = omega_;
+  pol = pol_; ordering = FDFD_ORDER_FB; omega = omega_; omega_pml = omega_;
   hc = hc_;
   ARG_CHECK(ctx, (int64_t)hc.cxm.size() == nx && (int64_t)hc.cxp.size() == nx && (int64_t)hc.cym.size() == ny && (int64_t)hc.cyp.size() == ny,
             "internal: level coefficient arrays do not match the level size");
   const int64_t N = nx * ny;
+  const double eps0 = kEps0 * g.L0, mu0 = kMu0 * g.L0;
   CUDA_TRY(ctx, c1d.alloc(2 * nx + 2 * ny));
   std::vector<std::complex<double>> pack;
   pack.insert(pack.end(), hc.cxm.begin(), hc.cxm.end()); pack.insert(pack.end(), hc.cxp.begin(), hc.cxp.end());
   pack.insert(pack.end(), hc.cym.begin(), hc.cym.end()); pack.insert(pack.end(), hc.cyp.begin(), hc.cyp.end());
   CUDA_TRY(ctx, cudaMemcpyAsync(c1d.p, pack.data(), pack.size() * sizeof(c128), cudaMemcpyHostToDevice, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // pack is a local
-  CUDA_TRY(ctx, mass.alloc(N));
   const int threads = 256;
   const int blocks = (int)std::min<int64_t>((N + threads - 1) / threads, (int64_t)ctx->num_sms * 16);
-  k_setup_tm<<<blocks, threads, 0, ctx->stream>>>(N, omega * omega * kEps0 * g.L0, eps_dev, mass.p);
+  if (pol == FDFD_TM) {
+    CUDA_TRY(ctx, mass.alloc(N));
+    k_setup_tm<<<blocks, threads, 0, ctx->stream>>>(N, omega * omega * eps0, eps_dev, mass.p);
+  } else {
+    CUDA_TRY(ctx, gx.alloc(N)); CUDA_TRY(ctx, gy.alloc(N));
+    k_setup_te<<<blocks, threads, 0, ctx->stream>>>(nx, ny, eps0, eps_dev, gx.p, gy.p);
+    mass_const = c128(omega * omega * mu0, 0.0);
+  }
   KLAUNCH(ctx);
   CUDA_TRY(ctx, cudaGetLastError());
   return FDFD_OK;

@@ -52,7 +52,7 @@ enum { FDFD_CSR = 0, FDFD_CSC = 1 };
 /* BICGSTAB: any preconditioner.  COCG: on the symmetrised system diag(sxf*syf) A, Jacobi or no preconditioner. */
 /* MLKRYLOV (opt-in; csrc/mlkrylov.cu, compiled but not yet run on a GPU): multilevel Krylov -- flexible GMRES on every level,
  * preconditioned by the multigrid cycle plus a coarse-grid Helmholtz correction solved by the same method one level down.
- * TM, FDFD_PRECOND_MG, FDFD_MG_F32 only. */
+ * TM and TE; FDFD_PRECOND_MG and FDFD_MG_F32 only. */
 enum { FDFD_SOLVER_BICGSTAB = 0, FDFD_SOLVER_COCG = 1, FDFD_SOLVER_MLKRYLOV = 2 };
 enum { FDFD_PRECOND_NONE = 0, FDFD_PRECOND_JACOBI = 1, FDFD_PRECOND_MG = 2 };
 enum { FDFD_MG_F32 = 0, FDFD_MG_F64 = 1 };

@@ -81,6 +81,18 @@ def test_mlkrylov_zero_source_and_bad_arguments(fdfd):
     f = fdfd.solve(d, fdfd.TM, solver=fdfd._lib.SOLVER_MLKRYLOV)
     assert f.info["flag"] == 0 and np.all(f.data == 0)
     with pytest.raises(fdfd.FdfdError):
-        fdfd.solve(d, fdfd.TE, solver=fdfd._lib.SOLVER_MLKRYLOV)                    # TM only
-    with pytest.raises(fdfd.FdfdError):
         fdfd.solve(d, fdfd.TM, solver=fdfd._lib.SOLVER_MLKRYLOV, mg_precision=1)     # fp32 multigrid only
+
+
+def test_mlkrylov_te_vs_oracle(fdfd):
+    """TE (driven.jl:45-51): the level operators carry the inverse averaged eps of their level"""
+    from oracle import fdfd_oracle as O
+    g = fdfd.Grid(0.02, [15, 15], [0.0, 3.84], [0.0, 2.56])
+    d = fdfd.Device(g, W200)
+    fdfd.setup_eps_r(d, [fdfd.Cylinder((1.9, 1.3), 0.5, 6.0)])
+    fdfd.setup_src(d, fdfd.Point(0.8, 1.0))
+    f = fdfd.solve(d, fdfd.TE, solver=fdfd._lib.SOLVER_MLKRYLOV)
+    assert f.info["flag"] == 0 and f.info["relres"] <= RES_TOL
+    go = O.Grid2D(0.02, [15, 15], [0.0, 3.84], [0.0, 2.56])
+    do = O.Device(go, [W200]); do.eps_r[:] = d.eps_r; do.src[:] = d.src
+    assert rel(f.data, O.solve(do, O.TE)["data"]) <= FIELD_TOL
