@@ -66,7 +66,7 @@ EXPORTS = [
     "fdfd_comm_unique_id", "fdfd_comm_create_nccl", "fdfd_comm_group_create", "fdfd_comm_group_destroy",
     "fdfd_comm_create_threads", "fdfd_comm_destroy", "fdfd_slab_rows", "fdfd_solve_driven_slab", "fdfd_comm_stats",
     "fdfd_solve_modulated_slab", "fdfd_eigenfrequency_slab", "fdfd_problem_ml_cycles",
-    "fdfd_debug_ml_lsq", "fdfd_debug_ml_transfer",
+    "fdfd_debug_ml_lsq", "fdfd_debug_ml_transfer", "fdfd_debug_ml_lsq_gpu", "fdfd_debug_ml_transfer_gpu",
 ]
 COMM_THREADS, COMM_NCCL = 0, 1
 COMM_ID_BYTES = 128
@@ -112,6 +112,8 @@ def lib():
         L.fdfd_problem_ml_cycles.argtypes = [vp, C.POINTER(i64)]
         L.fdfd_debug_ml_lsq.argtypes = [i32, vp, dbl, vp, C.POINTER(dbl)]
         L.fdfd_debug_ml_transfer.argtypes = [i64, i64, i32, dbl, vp, vp]
+        L.fdfd_debug_ml_lsq_gpu.argtypes = [vp, i32, vp, dbl, vp, C.POINTER(dbl)]
+        L.fdfd_debug_ml_transfer_gpu.argtypes = [vp, i64, i64, i32, dbl, vp, vp]
         L.fdfd_problem_get_history.argtypes = [vp, vp, i32, C.POINTER(i32)]
         L.fdfd_debug_hess_eig.argtypes = [i32, vp, vp, vp]
         L.fdfd_problem_flux_x.argtypes = [vp, dbl, dbl, dbl, i32, C.POINTER(dbl)]

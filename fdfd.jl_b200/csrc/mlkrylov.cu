@@ -507,3 +507,39 @@ extern "C" int fdfd_debug_ml_transfer(int64_t nx, int64_t ny, int mode, double s
   else { for (int64_t n = 0; n < nx * ny; ++n) o[n] = prolong_point(n, nx, ncx, ncy, a); }
   return FDFD_OK;
 }
+
+// the same two cores run by their device kernels (GPU needed): lets a test compare device and host results entry by entry
+extern "C" int fdfd_debug_ml_lsq_gpu(fdfd_ctx* ctx, int k, const fdfd_c128* H, double beta, fdfd_c128* y, double* resnorm) {
+  ARG_CHECK(ctx, ctx != nullptr, "ctx is NULL");
+  ARG_CHECK(ctx, k >= 1 && k <= kMaxK && H && y, "bad arguments");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  DevBuf<c128> dH, dy, dsc, dscr;
+  CUDA_TRY(ctx, dH.alloc((size_t)(k + 1) * k)); CUDA_TRY(ctx, dy.alloc(k)); CUDA_TRY(ctx, dsc.alloc(2));
+  CUDA_TRY(ctx, dscr.alloc((size_t)k * (k + 1) / 2 + 3 * (size_t)k + 2));
+  const c128 hb[2] = {c128(beta, 0.0), c128(0.0, 0.0)};
+  FDFD_TRY(fdfd_copy_in(ctx, dH.p, H, sizeof(c128) * (size_t)(k + 1) * k));
+  CUDA_TRY(ctx, cudaMemcpyAsync(dsc.p, hb, sizeof(hb), cudaMemcpyHostToDevice, ctx->stream));
+  k_ml_lsq<<<1, 32, 0, ctx->stream>>>(k, k + 1, dH.p, dsc.p, dy.p, dsc.p + 1, dscr.p, k); KLAUNCH(ctx);
+  CUDA_TRY(ctx, cudaGetLastError());
+  c128 hr[2];
+  CUDA_TRY(ctx, cudaMemcpyAsync(hr, dsc.p, sizeof(hr), cudaMemcpyDeviceToHost, ctx->stream));
+  FDFD_TRY(fdfd_copy_out(ctx, y, dy.p, sizeof(c128) * k));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (resnorm) *resnorm = hr[1].x;
+  return FDFD_OK;
+}
+extern "C" int fdfd_debug_ml_transfer_gpu(fdfd_ctx* ctx, int64_t nx, int64_t ny, int mode, double scale, const fdfd_c128* in, fdfd_c128* out) {
+  ARG_CHECK(ctx, ctx != nullptr, "ctx is NULL");
+  ARG_CHECK(ctx, nx >= 2 && ny >= 2 && in && out, "bad arguments");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const int64_t ncx = (nx + 1) / 2, ncy = (ny + 1) / 2, Nf = nx * ny, Nc = ncx * ncy;
+  DevBuf<c128> din, dout;
+  CUDA_TRY(ctx, din.alloc(mode == 0 ? Nf : Nc)); CUDA_TRY(ctx, dout.alloc(mode == 0 ? Nc : Nf));
+  FDFD_TRY(fdfd_copy_in(ctx, din.p, in, sizeof(c128) * (size_t)(mode == 0 ? Nf : Nc)));
+  if (mode == 0) { k_ml_restrict<<<vec_blocks_for(ctx, Nc), 256, 0, ctx->stream>>>(nx, ny, ncx, ncy, din.p, dout.p, scale); KLAUNCH(ctx); }
+  else { k_ml_prolong<<<vec_blocks_for(ctx, Nf), 256, 0, ctx->stream>>>(nx, ny, ncx, ncy, din.p, dout.p); KLAUNCH(ctx); }
+  CUDA_TRY(ctx, cudaGetLastError());
+  FDFD_TRY(fdfd_copy_out(ctx, out, dout.p, sizeof(c128) * (size_t)(mode == 0 ? Nc : Nf)));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return FDFD_OK;
+}

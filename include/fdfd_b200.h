@@ -265,6 +265,9 @@ int fdfd_debug_hess_eig(int n, const fdfd_c128* H, fdfd_c128* evals, fdfd_c128* 
  * and its vertex-centred coarse grid ((nx+1)/2, (ny+1)/2): mode 0 = scale * Z^T (fine -> coarse), mode 1 = Z (coarse -> fine). */
 int fdfd_debug_ml_lsq(int k, const fdfd_c128* H, double beta, fdfd_c128* y, double* resnorm);
 int fdfd_debug_ml_transfer(int64_t nx, int64_t ny, int mode, double scale, const fdfd_c128* in, fdfd_c128* out);
+/* the same two cores run by their device kernels (GPU needed; host or device buffers) -- device/host comparison hooks */
+int fdfd_debug_ml_lsq_gpu(fdfd_ctx* ctx, int k, const fdfd_c128* H, double beta, fdfd_c128* y, double* resnorm);
+int fdfd_debug_ml_transfer_gpu(fdfd_ctx* ctx, int64_t nx, int64_t ny, int mode, double scale, const fdfd_c128* in, fdfd_c128* out);
 
 #ifdef __cplusplus
 }

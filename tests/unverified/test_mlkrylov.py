@@ -96,3 +96,31 @@ def test_mlkrylov_te_vs_oracle(fdfd):
     go = O.Grid2D(0.02, [15, 15], [0.0, 3.84], [0.0, 2.56])
     do = O.Device(go, [W200]); do.eps_r[:] = d.eps_r; do.src[:] = d.src
     assert rel(f.data, O.solve(do, O.TE)["data"]) <= FIELD_TOL
+
+
+def test_mlkrylov_device_cores_match_host(fdfd, ctx):
+    """the device kernels of the least-squares solve and of the grid transfers against their host twins (which
+    tests/test_cabi_cpu.py checks against NumPy): first thing to look at if a multilevel solve misbehaves"""
+    import ctypes as C
+    from fdfd_jl_b200._lib import ptr
+    L = fdfd.lib()
+    rng = np.random.default_rng(5)
+    for k in (1, 6, 12, 40):
+        H = np.zeros((k + 1, k), complex)
+        for j in range(k):
+            H[:j + 2, j] = rng.standard_normal(j + 2) + 1j * rng.standard_normal(j + 2)
+        Hf = np.asfortranarray(H)
+        yh, yd = np.zeros(k, complex), np.zeros(k, complex)
+        rh, rd = C.c_double(), C.c_double()
+        assert L.fdfd_debug_ml_lsq(k, ptr(Hf), 0.8, ptr(yh), C.byref(rh)) == 0
+        fdfd._lib.check(L.fdfd_debug_ml_lsq_gpu(ctx.handle, k, ptr(Hf), 0.8, ptr(yd), C.byref(rd)), ctx.handle)
+        assert np.abs(yh - yd).max() <= 1e-9 * max(1.0, np.abs(yh).max()) and abs(rh.value - rd.value) <= 1e-12   # fma contraction differs
+    for nx, ny in ((64, 48), (65, 33), (256, 255)):
+        ncx, ncy = (nx + 1) // 2, (ny + 1) // 2
+        v = np.asfortranarray(rng.standard_normal((nx, ny)) + 1j * rng.standard_normal((nx, ny)))
+        y = np.asfortranarray(rng.standard_normal((ncx, ncy)) + 1j * rng.standard_normal((ncx, ncy)))
+        for mode, src, shape in ((0, v, (ncx, ncy)), (1, y, (nx, ny))):
+            oh, od = np.zeros(shape, complex, order="F"), np.zeros(shape, complex, order="F")
+            assert L.fdfd_debug_ml_transfer(nx, ny, mode, 0.25, ptr(src), ptr(oh)) == 0
+            fdfd._lib.check(L.fdfd_debug_ml_transfer_gpu(ctx.handle, nx, ny, mode, 0.25, ptr(src), ptr(od)), ctx.handle)
+            assert np.abs(oh - od).max() <= 1e-15
