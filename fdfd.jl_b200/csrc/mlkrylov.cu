@@ -17,8 +17,9 @@
 // Level 0 works on the reference operator itself in fp64, checks the TRUE residual ||b - A x|| / ||b|| and restarts.
 // All Gram-Schmidt coefficients, the Hessenberg matrix and the small least-squares solve stay on the device.
 //
-// CPU prototype numbers (synthetic TM map, multigrid cycles needed to reach 1e-10, tools/multilevel_prototype.py):
-//   1024^2: BiCGSTAB + cycle (the default solver) 474 fine cycles; spec (.,6,6): 31 fine + 186 level-1 + 2232 level-2 cycles.
+// CPU prototype numbers (bench map, multigrid cycles started per level to reach 1e-10, tools/multilevel_prototype.py):
+//   1024^2: default solver 474 fine cycles; steps (6,12): 24 fine + 144 level-1 + 1728 level-2;  (6,8): 26 + 156 + 1248.
+//   2048^2: default solver 960 fine cycles; steps (6,8): 47 + 282 + 2256;  (8,12): 32 + 256 + 3072  (DESIGN.md 5b).
 //
 // STATUS: written in a session without GPU access -- compiles for sm_100a, exercised by tests/unverified/ only.
 #include "krylov.cuh"

@@ -15,6 +15,9 @@ from oracle import fdfd_oracle as O
 from tools.mg_prototype import MG, Level, synth_device, bicgstab as bicgstab_mf
 
 
+T0 = time.time()
+
+
 def prolong1d(n):
     nc = n // 2
     rows, cols, vals = [], [], []
@@ -23,7 +26,7 @@ def prolong1d(n):
     return sp.csr_matrix((vals, (rows, cols)), shape=(n, nc))
 
 
-def fgmres_fixed(A, b, prec, tol, maxit, restart=60):
+def fgmres_fixed(A, b, prec, tol, maxit, restart=60, log=False):
     """flexible GMRES, stops at tol (relative to ||b||) or after maxit preconditioner applications"""
     x = np.zeros_like(b); nb = np.linalg.norm(b); total = 0
     if nb == 0: return x, 0
@@ -39,6 +42,7 @@ def fgmres_fixed(A, b, prec, tol, maxit, restart=60):
             H[k + 1, k] = np.linalg.norm(w); V.append(w / H[k + 1, k])
             y, *_ = np.linalg.lstsq(H[:k + 2, :k + 1], g[:k + 2], rcond=None)
             res = np.linalg.norm(H[:k + 2, :k + 1] @ y - g[:k + 2]) / nb
+            if log: print(f"    outer {total:3d} relres {res:.2e}  ({time.time() - T0:.0f}s)", flush=True)
             if res <= tol: break
         for i in range(len(y)): x = x + y[i] * Zs[i]
         if res <= tol: break
@@ -86,7 +90,7 @@ def main():
             gc = (Zs[l].T @ v.ravel()).reshape(nx // 2, ny // 2) / 4.0
             q = (Zs[l] @ solve(l + 1, gc, inner_tol).ravel()).reshape(nx, ny)
             return q + Minv(l)(v - A(l)(q))
-        x, k = fgmres_fixed(A(l), rhs, T, tol, spec[l])
+        x, k = fgmres_fixed(A(l), rhs, T, tol, spec[l], log=(l == 0 and bool(os.environ.get("PROGRESS"))))
         if l == 0: print(f"  outer iterations: {k}", flush=True)
         return x
 
