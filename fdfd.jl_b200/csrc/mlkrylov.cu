@@ -424,6 +424,7 @@ int krylov_multilevel(fdfd_problem* P, fdfd_info_t* info) {
   FDFD_TRY(fetch(L.sc.p + 2, 1));
   const double bnorm = hs[0].x;
   int its = 0, restarts = 0, flag = FDFD_ERR_NOCONV;
+  std::vector<double> hist(1, bnorm * bnorm);   // ||r_k||^2 (FGMRES estimate) per outer iteration, for fdfd_problem_get_history
   double rel = 0.0;
   if (bnorm == 0.0) { flag = FDFD_OK; }   // b = 0 -> x = 0
   else {
@@ -442,6 +443,7 @@ int krylov_multilevel(fdfd_problem* P, fdfd_info_t* info) {
         k_ml_lsq<<<1, 32, 0, st>>>(j, L.k + 1, L.H.p, L.sc.p, L.y.p, L.sc.p + 1, L.lsq.p, L.k); KLAUNCH(ctx);
         FDFD_TRY(fetch(L.sc.p + 1, 1));
         const double est = hs[0].x / bnorm;
+        hist.push_back(hs[0].x * hs[0].x);
         if (o.verbose) fprintf(stderr, "[fdfd_b200] multilevel Krylov it %d estimated relres %.3e\n", its, est);
         if (!std::isfinite(est)) { flag = FDFD_ERR_BREAKDOWN; break; }
         if (est <= o.tol) break;
@@ -468,6 +470,12 @@ int krylov_multilevel(fdfd_problem* P, fdfd_info_t* info) {
   float ms = 0;
   cudaEventElapsedTime(&ms, e0, e1);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
+  {  // residual history in the layout of the BiCGSTAB loop (KrylovWork::hist, h_scal)
+    const size_t cnt = std::min(hist.size(), P->w.hist.n);
+    cudaMemcpyAsync(P->w.hist.p, hist.data(), cnt * sizeof(double), cudaMemcpyHostToDevice, st);
+    cudaStreamSynchronize(st);   // hist is a local
+    P->w.h_scal->iter = (int)cnt - 1; P->w.h_scal->bnorm2 = bnorm * bnorm;
+  }
   info->iters = its;
   info->relres = rel;
   info->flag = flag;
