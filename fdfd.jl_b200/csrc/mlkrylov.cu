@@ -407,10 +407,10 @@ int krylov_multilevel(fdfd_problem* P, fdfd_info_t* info) {
   struct Restore { Multigrid<float>* mg; const int* d; ~Restore() { mg->done = d; } } restore{P->mgf, saved_done};
   std::fill(M.cycles, M.cycles + 8, 0);
 
-  cudaEvent_t e0, e1;
-  CUDA_TRY(ctx, cudaEventCreate(&e0)); CUDA_TRY(ctx, cudaEventCreate(&e1));
+  struct Events { cudaEvent_t e0 = nullptr, e1 = nullptr; ~Events() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); } } ev;
+  CUDA_TRY(ctx, cudaEventCreate(&ev.e0)); CUDA_TRY(ctx, cudaEventCreate(&ev.e1));
   const int64_t launches0 = ctx->launches;
-  CUDA_TRY(ctx, cudaEventRecord(e0, st));
+  CUDA_TRY(ctx, cudaEventRecord(ev.e0, st));
 
   c128* b = P->w.b.p; c128* x = P->w.x.p; c128* r = P->w.r.p; c128* t = P->w.t.p;
   c128 hs[2];
@@ -465,11 +465,10 @@ int krylov_multilevel(fdfd_problem* P, fdfd_info_t* info) {
       ++restarts;
     }
   }
-  cudaEventRecord(e1, st);
-  cudaEventSynchronize(e1);
+  cudaEventRecord(ev.e1, st);
+  cudaEventSynchronize(ev.e1);
   float ms = 0;
-  cudaEventElapsedTime(&ms, e0, e1);
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaEventElapsedTime(&ms, ev.e0, ev.e1);
   {  // residual history in the layout of the BiCGSTAB loop (KrylovWork::hist, h_scal)
     const size_t cnt = std::min(hist.size(), P->w.hist.n);
     cudaMemcpyAsync(P->w.hist.p, hist.data(), cnt * sizeof(double), cudaMemcpyHostToDevice, st);
