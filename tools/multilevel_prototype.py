@@ -26,6 +26,17 @@ def prolong1d(n):
     return sp.csr_matrix((vals, (rows, cols)), shape=(n, nc))
 
 
+def prolong1d_cubic(n):
+    """even fine points inject, odd ones take the 4-point cubic stencil (-1, 9, 9, -1)/16 (periodic)"""
+    nc = n // 2
+    rows, cols, vals = [], [], []
+    for I in range(nc):
+        rows += [2 * I]; cols += [I]; vals += [1.0]
+        for off, w in ((-1, -1 / 16), (0, 9 / 16), (1, 9 / 16), (2, -1 / 16)):
+            rows.append(2 * I + 1); cols.append((I + off) % nc); vals.append(w)
+    return sp.csr_matrix((vals, (rows, cols)), shape=(n, nc))
+
+
 def fgmres_fixed(A, b, prec, tol, maxit, restart=60, log=False):
     """flexible GMRES, stops at tol (relative to ||b||) or after maxit preconditioner applications"""
     x = np.zeros_like(b); nb = np.linalg.norm(b); total = 0
@@ -68,7 +79,8 @@ def main():
     for l in range(1, nlev):
         L = mg.levels[l]
         ops.append(Level(L.Nx, L.Ny, L.cxm, L.cxp, L.cym, L.cyp, L.mass / (1 - 1j * beta)))
-    Zs = [sp.kron(prolong1d(ops[l].Nx), prolong1d(ops[l].Ny), format="csr") for l in range(nlev - 1)]
+    P1 = prolong1d_cubic if os.environ.get("CUBIC") else prolong1d
+    Zs = [sp.kron(P1(ops[l].Nx), P1(ops[l].Ny), format="csr") for l in range(nlev - 1)]
     cntM = [0] * nlev; cntA = [0] * nlev
 
     def A(l):
