@@ -45,6 +45,32 @@ def test_no_cpu_fallback_for_slab(fdfd):
         fdfd.Context(0)
 
 
+def test_no_cpu_fallback_for_slab_modulated_eigen_and_multilevel(fdfd):
+    """the slab-sharded modulated / eigenfrequency entry points and the multilevel Krylov solver fail loudly without a GPU"""
+    import math
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from fdfd_jl_b200 import slab
+    g = fdfd.Grid(0.02, [10, 10], [0.0, 2.56], [0.0, 2.56])
+    md = fdfd.ModulatedDevice(g, 2 * math.pi * 200e12, 4.5e14, 1)
+    with pytest.raises(fdfd.FdfdError):
+        slab.solve_modulated_slabs_threads(md, 2)
+    with pytest.raises(fdfd.FdfdError):
+        slab.eigenfrequency_slabs_threads(fdfd.Device(g, 2 * math.pi * 200e12), 2, 2)
+    with pytest.raises(fdfd.FdfdError):
+        fdfd.solve(fdfd.Device(g, 2 * math.pi * 200e12), fdfd.TM, solver=fdfd._lib.SOLVER_MLKRYLOV)
+    # NULL / out-of-range arguments of the new entry points are rejected before any device work
+    import ctypes as C
+    L = fdfd.lib()
+    gc = g.as_c()
+    assert L.fdfd_solve_modulated_slab(None, None, C.byref(gc), 1.0, 1.0, 1, 1, None, None, None, None, None, None) == fdfd._lib.ERR_ARG
+    assert L.fdfd_eigenfrequency_slab(None, None, C.byref(gc), fdfd.TM, 1.0, 1, 0, 0, None, None, None, None, None) == fdfd._lib.ERR_ARG
+    assert L.fdfd_problem_ml_cycles(None, None) == fdfd._lib.ERR_ARG
+    assert L.fdfd_debug_ml_lsq(0, None, 1.0, None, None) == fdfd._lib.ERR_ARG
+    assert L.fdfd_debug_ml_transfer(1, 1, 0, 1.0, None, None) == fdfd._lib.ERR_ARG
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
