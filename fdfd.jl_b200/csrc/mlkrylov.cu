@@ -66,6 +66,44 @@ __global__ void k_ml_combine(int64_t N, int k, const c128* __restrict__ y, const
     x[i] = s;
   }
 }
+// ---- fused classical Gram-Schmidt pass of the inner levels (measured in the prototype: same outer iteration count as modified
+// Gram-Schmidt, tools/multilevel_prototype.py CGS=1): all <V_v, w> of a chunk in one pass over w, then one pass subtracting them
+constexpr int kMD = 8;   // basis vectors per launch
+struct VecPtrs { const c128* p[kMD]; };
+__global__ void __launch_bounds__(kT) k_ml_multidot(int64_t N, int nv, VecPtrs V, const c128* __restrict__ w, double* __restrict__ partials) {
+  double acc[2 * kMD];
+#pragma unroll
+  for (int v = 0; v < 2 * kMD; ++v) acc[v] = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x; i < N; i += (int64_t)gridDim.x * kT) {
+    const c128 wi = w[i];
+#pragma unroll
+    for (int v = 0; v < kMD; ++v) {
+      if (v < nv) { const c128 q = cmulc(V.p[v][i], wi); acc[2 * v] += q.x; acc[2 * v + 1] += q.y; }
+    }
+  }
+  block_reduce_store<kT, 2 * kMD>(acc, partials + (size_t)blockIdx.x * 2 * kMD);
+}
+// one CTA per dot product: out[v] = sum over the nb block partials (fixed order)
+__global__ void __launch_bounds__(kT) k_ml_multidot_final(const double* __restrict__ partials, int nb, c128* __restrict__ out) {
+  const int v = blockIdx.x;
+  double acc[2] = {0.0, 0.0};
+  for (int b = threadIdx.x; b < nb; b += kT) { acc[0] += partials[(size_t)b * 2 * kMD + 2 * v]; acc[1] += partials[(size_t)b * 2 * kMD + 2 * v + 1]; }
+  block_reduce_store<kT, 2>(acc, reinterpret_cast<double*>(out + v));
+}
+// w -= sum_v coef[v] V_v
+__global__ void k_ml_multiaxpy(int64_t N, int nv, const c128* __restrict__ coef, VecPtrs V, c128* __restrict__ w) {
+  c128 c[kMD];
+#pragma unroll
+  for (int v = 0; v < kMD; ++v) c[v] = v < nv ? coef[v] : c128(0.0, 0.0);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    c128 s = w[i];
+#pragma unroll
+    for (int v = 0; v < kMD; ++v) {
+      if (v < nv) { const c128 t = c[v] * V.p[v][i]; s -= t; }
+    }
+    w[i] = s;
+  }
+}
 // r = b - t, partial ||r||^2
 __global__ void __launch_bounds__(kT) k_ml_resid(int64_t N, const c128* __restrict__ b, const c128* __restrict__ t, c128* __restrict__ r, double* __restrict__ partials) {
   double acc[2] = {0, 0};
@@ -214,6 +252,7 @@ struct MLKrylov {
   std::vector<std::unique_ptr<MLLevel>> lev;
   std::map<std::vector<void*>, IterGraph> graphs;   // the level-1 solve, one graph per multigrid buffer-rotation state
   bool use_graph = false;
+  bool fused_gs = true;                              // inner levels: fused classical Gram-Schmidt (FDFD_ML_MGS=1 selects the modified one)
   int64_t cycles[8] = {0, 0, 0, 0, 0, 0, 0, 0};      // multigrid cycles started per level (diagnostics)
   ~MLKrylov() { for (auto& kv : graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec); }
 };
@@ -261,10 +300,11 @@ int ml_setup(fdfd_problem* P, MLKrylov& M) {
     if (l + 1 < nl) { MALLOC(L.q, L.N); MALLOC(L.t, L.N); }
     MALLOC(L.H, (size_t)(L.k + 1) * L.k); MALLOC(L.y, L.k); MALLOC(L.sc, 4);
     MALLOC(L.lsq, (size_t)L.k * (L.k + 1) / 2 + 3 * (size_t)L.k + 2);
-    MALLOC(L.parts, (size_t)L.nb * 2);
+    MALLOC(L.parts, (size_t)L.nb * 2 * kMD);
   }
   cudaStream_t st = ctx->stream;
   M.use_graph = P->opts.use_graph && st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
+  if (const char* e = getenv("FDFD_ML_MGS")) M.fused_gs = atoi(e) == 0;   // diagnostics
   return FDFD_OK;
 }
 
@@ -313,9 +353,25 @@ int ml_arnoldi_step(MLKrylov& M, int li, int j) {
   DotSpec d0;
   FDFD_TRY(launch_apply(ctx, L.op->view(), L.op->pol == FDFD_TE, L.Z[j].p, false, L.w.p, d0));
   c128* Hj = L.H.p + (size_t)j * (L.k + 1);
-  for (int i = 0; i <= j; ++i) {
-    FDFD_TRY(ml_dot(ctx, L, L.V[i].p, L.w.p, Hj + i, 0));
-    k_ml_axpy_neg<<<L.nb, 256, 0, st>>>(L.N, Hj + i, L.V[i].p, L.w.p); KLAUNCH(ctx);
+  if (li == 0 || !M.fused_gs) {   // modified Gram-Schmidt (level 0 always: its basis is long and its tolerance tight)
+    for (int i = 0; i <= j; ++i) {
+      FDFD_TRY(ml_dot(ctx, L, L.V[i].p, L.w.p, Hj + i, 0));
+      k_ml_axpy_neg<<<L.nb, 256, 0, st>>>(L.N, Hj + i, L.V[i].p, L.w.p); KLAUNCH(ctx);
+    }
+  } else {                        // one classical pass in chunks of kMD vectors: every dot is taken against the same w
+    for (int v0 = 0; v0 <= j; v0 += kMD) {
+      const int nv = std::min(kMD, j + 1 - v0);
+      VecPtrs vp;
+      for (int v = 0; v < kMD; ++v) vp.p[v] = L.V[v0 + (v < nv ? v : 0)].p;
+      k_ml_multidot<<<L.nb, kT, 0, st>>>(L.N, nv, vp, L.w.p, L.parts.p); KLAUNCH(ctx);
+      k_ml_multidot_final<<<nv, kT, 0, st>>>(L.parts.p, L.nb, Hj + v0); KLAUNCH(ctx);
+    }
+    for (int v0 = 0; v0 <= j; v0 += kMD) {
+      const int nv = std::min(kMD, j + 1 - v0);
+      VecPtrs vp;
+      for (int v = 0; v < kMD; ++v) vp.p[v] = L.V[v0 + (v < nv ? v : 0)].p;
+      k_ml_multiaxpy<<<L.nb, 256, 0, st>>>(L.N, nv, Hj + v0, vp, L.w.p); KLAUNCH(ctx);
+    }
   }
   FDFD_TRY(ml_dot(ctx, L, L.w.p, L.w.p, Hj + j + 1, 1));
   k_ml_scale_inv<<<L.nb, 256, 0, st>>>(L.N, Hj + j + 1, L.w.p, L.V[j + 1].p); KLAUNCH(ctx);

@@ -124,3 +124,14 @@ def test_mlkrylov_device_cores_match_host(fdfd, ctx):
             assert L.fdfd_debug_ml_transfer(nx, ny, mode, 0.25, ptr(src), ptr(oh)) == 0
             fdfd._lib.check(L.fdfd_debug_ml_transfer_gpu(ctx.handle, nx, ny, mode, 0.25, ptr(src), ptr(od)), ctx.handle)
             assert np.abs(oh - od).max() <= 1e-15
+
+
+def test_mlkrylov_fused_and_modified_gram_schmidt_agree(fdfd, monkeypatch):
+    """inner levels: the fused classical Gram-Schmidt pass (default) against modified Gram-Schmidt (FDFD_ML_MGS=1)"""
+    d = waveguide(fdfd, 256, 128)
+    a = fdfd.solve(d, fdfd.TM, solver=fdfd._lib.SOLVER_MLKRYLOV)
+    monkeypatch.setenv("FDFD_ML_MGS", "1")
+    b = fdfd.solve(d, fdfd.TM, solver=fdfd._lib.SOLVER_MLKRYLOV)
+    assert a.info["flag"] == 0 and b.info["flag"] == 0
+    assert abs(a.info["iters"] - b.info["iters"]) <= 2
+    assert rel(a.data, b.data) <= FIELD_TOL

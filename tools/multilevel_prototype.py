@@ -48,8 +48,12 @@ def fgmres_fixed(A, b, prec, tol, maxit, restart=60, log=False):
         V = [r / beta]; Zs = []; H = np.zeros((m + 1, m), complex); g = np.zeros(m + 1, complex); g[0] = beta
         for k in range(m):
             z = prec(V[k]); Zs.append(z); w = A(z); total += 1
-            for i in range(k + 1):
-                H[i, k] = np.vdot(V[i], w); w = w - H[i, k] * V[i]
+            if os.environ.get("CGS") and not log:   # classical Gram-Schmidt, one pass (inner levels only): all dots against the same w
+                h = [np.vdot(V[i], w) for i in range(k + 1)]
+                for i in range(k + 1): H[i, k] = h[i]; w = w - h[i] * V[i]
+            else:
+                for i in range(k + 1):
+                    H[i, k] = np.vdot(V[i], w); w = w - H[i, k] * V[i]
             H[k + 1, k] = np.linalg.norm(w); V.append(w / H[k + 1, k])
             y, *_ = np.linalg.lstsq(H[:k + 2, :k + 1], g[:k + 2], rcond=None)
             res = np.linalg.norm(H[:k + 2, :k + 1] @ y - g[:k + 2]) / nb
