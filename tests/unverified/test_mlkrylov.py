@@ -135,3 +135,17 @@ def test_mlkrylov_fused_and_modified_gram_schmidt_agree(fdfd, monkeypatch):
     assert a.info["flag"] == 0 and b.info["flag"] == 0
     assert abs(a.info["iters"] - b.info["iters"]) <= 2
     assert rel(a.data, b.data) <= FIELD_TOL
+
+
+def test_eigenfrequency_with_multilevel_inner_solves(fdfd):
+    """shift-invert Arnoldi (eigen.jl:69-96) whose inner solves run the multilevel Krylov solver (tol 1e-11)"""
+    g = fdfd.Grid(0.02, [15, 15], [-2.0, 2.0], [-2.0, 2.0])
+    d = fdfd.Device(g, W200)
+    fdfd.setup_eps_r(d, [fdfd.Cylinder((0, 0), 0.8, 1.0), fdfd.Cylinder((0, 0), 1.0, 12.25)])  # notebook cell 31
+    om_ref, _ = fdfd.eigenfrequency(d, fdfd.TM, 6, which="LM")
+    om, _ = fdfd.eigenfrequency(d, fdfd.TM, 4, which="LM", solver=fdfd._lib.SOLVER_MLKRYLOV)
+    ref = list(om_ref)
+    for z in om:
+        k = int(np.argmin([abs(z - r) for r in ref]))
+        assert abs(z - ref[k]) / abs(ref[k]) <= 1e-8
+        ref.pop(k)
