@@ -3,7 +3,10 @@
 * notebook_example3.json -- the reference's only known-answer numbers (notebooks/Example_simulations.ipynb cells 21/23/25),
   copied from the notebook outputs, plus the oracle's reproduction of them.
 * tm_small.npz / te_small.npz / mod_small.npz -- small seeded problems: inputs, CSR of the system matrix and the solved
-  (Nx,Ny,3) fields, so the GPU tests can also be checked against committed vectors."""
+  (Nx,Ny,3) fields, so the GPU tests can also be checked against committed vectors.
+* eig_ring.json -- eigenfrequency() of the notebook's ring resonator (cell 31: Cylinder R=1.0 eps 12.25 with an R=0.8 air core,
+  4 x 4 um, Npml 15) at 200^2 and 400^2, TM and TE, 6 modes :LM.  The 400^2 values are the regression values SURVEY.md §8c
+  records from its probe of the same restatement; they are NOT reference-published numbers (the reference has none for this path)."""
 import json
 import math
 import os
@@ -43,7 +46,24 @@ def modulated_small():
                 src=d.src, fields=np.stack([x["data"] for x in f], axis=3))
 
 
+def eig_ring():
+    out = {"source": "oracle (SciPy ARPACK shift-invert, eigen.jl:69-115 restated); 400^2 values = SURVEY.md section 8c probe values",
+           "geometry": "Grid(4/n, [15,15], [-2,2], [-2,2]); Cylinder((0,0),0.8,eps 1) over Cylinder((0,0),1.0,eps 12.25); omega0 = 2 pi 200e12; nev 6, which LM"}
+    for n in (200, 400):
+        g = O.Grid2D(4.0 / n, [15, 15], [-2.0, 2.0], [-2.0, 2.0])
+        d = O.Device(g, [W])
+        xs, ys = O.xc(g)[:, None], O.yc(g)[None, :]
+        r2 = xs ** 2 + ys ** 2
+        d.eps_r[r2 <= 1.0] = 12.25
+        d.eps_r[r2 <= 0.64] = 1.0          # the air core is listed first in the notebook: first shape wins (device.jl:47-61)
+        for pol, name in ((O.TM, "TM"), (O.TE, "TE")):
+            om, _ = O.eigenfrequency(d, pol, 6, which="LM", v0=np.ones(len(g), dtype=complex))
+            out[f"{name}_{n}"] = [[float(z.real), float(z.imag)] for z in om]
+    return out
+
+
 if __name__ == "__main__":
+    json.dump(eig_ring(), open(os.path.join(HERE, "eig_ring.json"), "w"), indent=1)
     np.savez_compressed(os.path.join(HERE, "tm_small.npz"), **small(O.TM))
     np.savez_compressed(os.path.join(HERE, "te_small.npz"), **small(O.TE))
     np.savez_compressed(os.path.join(HERE, "mod_small.npz"), **modulated_small())
