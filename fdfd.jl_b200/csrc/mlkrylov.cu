@@ -266,12 +266,12 @@ int ml_setup(fdfd_problem* P, MLKrylov& M) {
   fdfd_ctx* ctx = P->ctx;
   Multigrid<float>* mg = P->mgf;
   M.P = P;
-  // spec: ml_spec bytes = k1 | k2 << 8 | k3 << 16 | restart << 24 ; 0 -> (6, 12, -, 40).  Levels beyond the hierarchy are dropped.
+  // spec: ml_spec bytes = k1 | k2 << 8 | k3 << 16 | restart << 24 ; 0 -> (6, 12, -, 48).  Levels beyond the hierarchy are dropped.
   uint32_t spec = (uint32_t)P->opts.ml_spec;
   if (const char* e = getenv("FDFD_ML_SPEC")) spec = (uint32_t)strtoul(e, nullptr, 0);   // diagnostics
   int ks[4] = {(int)(spec >> 24) & 0xff, (int)spec & 0xff, (int)(spec >> 8) & 0xff, (int)(spec >> 16) & 0xff};
   if ((spec & 0xffffff) == 0) { ks[1] = 6; ks[2] = 12; ks[3] = 0; }
-  if (ks[0] == 0) ks[0] = 40;
+  if (ks[0] == 0) ks[0] = 48;
   int nl = 1;
   while (nl < 4 && ks[nl] > 0 && nl < mg->levels()) ++nl;
   for (int l = 0; l < nl; ++l) ARG_CHECK(ctx, ks[l] >= 1 && ks[l] <= kMaxK, "multilevel Krylov: iteration counts must be in [1, 128]");
