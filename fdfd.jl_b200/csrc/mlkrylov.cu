@@ -485,7 +485,8 @@ int krylov_multilevel(fdfd_problem* P, fdfd_info_t* info) {
   if (bnorm == 0.0) { flag = FDFD_OK; }   // b = 0 -> x = 0
   else {
     CUDA_TRY(ctx, cudaMemcpyAsync(r, b, N * sizeof(c128), cudaMemcpyDeviceToDevice, st));
-    double rnorm = bnorm;
+    double rnorm = bnorm, prev_rel = 1.0;
+    int stalled = 0;
     while (true) {
       // ---- one FGMRES cycle from the current residual r (||r|| = rnorm)
       const c128 hb(rnorm, 0.0);
@@ -518,6 +519,10 @@ int krylov_multilevel(fdfd_problem* P, fdfd_info_t* info) {
       if (std::isfinite(rel) && rel <= o.tol) { flag = FDFD_OK; break; }
       if (!std::isfinite(rel)) { flag = FDFD_ERR_BREAKDOWN; break; }
       if (its >= o.maxit) { flag = FDFD_ERR_NOCONV; break; }
+      // stagnation: four restart cycles in a row that each gained less than a factor 2 -> give up instead of running to maxit
+      stalled = rel > 0.5 * prev_rel ? stalled + 1 : 0;
+      prev_rel = rel;
+      if (stalled >= 4) { flag = FDFD_ERR_NOCONV; break; }
       ++restarts;
     }
   }
