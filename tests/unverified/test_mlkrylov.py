@@ -149,3 +149,16 @@ def test_eigenfrequency_with_multilevel_inner_solves(fdfd):
         k = int(np.argmin([abs(z - r) for r in ref]))
         assert abs(z - ref[k]) / abs(ref[k]) <= 1e-8
         ref.pop(k)
+
+
+def test_mlkrylov_thin_pml(fdfd):
+    """dh = 0.01, Npml = 10: the PML is thinner than a level-2 cell, the case that needed Galerkin-consistent multigrid
+    transfers.  The deflation transfers are plain bilinear; flexible GMRES must still converge."""
+    g = fdfd.Grid(0.01, [10, 10], [0.0, 3.84], [-0.96, 0.96])
+    d = fdfd.Device(g, W200)
+    fdfd.setup_eps_r(d, lambda x, y: abs(y) <= 0.15, 12.0)
+    fdfd.setup_src(d, fdfd.Point(0.6, 0.0), fdfd.XHAT)
+    ref = fdfd.solve(d, fdfd.TM)
+    f = fdfd.solve(d, fdfd.TM, solver=fdfd._lib.SOLVER_MLKRYLOV)
+    assert ref.info["flag"] == 0 and f.info["flag"] == 0 and f.info["relres"] <= RES_TOL
+    assert rel(f.data, ref.data) <= FIELD_TOL
