@@ -289,10 +289,12 @@ int ml_setup(fdfd_problem* P, MLKrylov& M) {
       MALLOC(L.rhs, L.N); MALLOC(L.x, L.N);
     }
     L.V.resize(L.k + 1); L.Z.resize(L.k);
-    for (auto& b : L.V) MALLOC(b, L.N);
-    for (auto& b : L.Z) MALLOC(b, L.N);
+    // level 0 grows its basis on demand (a solve that converges in 25 iterations must not hold 97 fine vectors: four
+    // concurrent 4096^2 solves would otherwise pin 104 GB); the inner levels are small and use every vector in every solve
+    if (l == 0) MALLOC(L.V[0], L.N);
+    else { for (auto& b : L.V) MALLOC(b, L.N); for (auto& b : L.Z) MALLOC(b, L.N); }
     std::vector<const c128*> zp(L.k);
-    for (int j = 0; j < L.k; ++j) zp[j] = L.Z[j].p;
+    for (int j = 0; j < L.k; ++j) zp[j] = L.Z[j].p;   // level 0: nullptr until the vector exists
     MALLOC(L.Zptr, L.k);
     CUDA_TRY(ctx, cudaMemcpyAsync(L.Zptr.p, zp.data(), L.k * sizeof(const c128*), cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // zp is a local
@@ -495,6 +497,13 @@ int krylov_multilevel(fdfd_problem* P, fdfd_info_t* info) {
       CUDA_TRY(ctx, cudaStreamSynchronize(st));   // hb is a local
       int j = 0;
       for (; j < L.k && its < o.maxit; ) {
+        if (!L.Z[j].p) {   // grow the basis
+          MALLOC(L.Z[j], N);
+          const c128* zp = L.Z[j].p;
+          CUDA_TRY(ctx, cudaMemcpyAsync(L.Zptr.p + j, &zp, sizeof(zp), cudaMemcpyHostToDevice, st));
+          CUDA_TRY(ctx, cudaStreamSynchronize(st));   // zp is a local
+        }
+        if (!L.V[j + 1].p) MALLOC(L.V[j + 1], N);
         FDFD_TRY(ml_arnoldi_step(M, 0, j));
         ++j; ++its;
         k_ml_lsq<<<1, 32, 0, st>>>(j, L.k + 1, L.H.p, L.sc.p, L.y.p, L.sc.p + 1, L.lsq.p, L.k); KLAUNCH(ctx);
