@@ -3,6 +3,11 @@ import sys
 
 import pytest
 
+# cap the BLAS / OpenMP pools before NumPy is imported: their threads busy-wait, so on a loaded host an un-capped pool makes the
+# SuperLU / ARPACK heavy oracle tests crawl (measured: 8 s -> minutes with four other busy cores).  An explicit setting wins.
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+    os.environ.setdefault(_v, str(min(4, os.cpu_count() or 1)))
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -118,3 +118,16 @@ def test_eigenfrequency_ring(fdfd, pol):
     _, fref = O.eigen_fields(do, Po, np.array([-(om[0] ** 2) * mu0 * (eps0 if pol == "TM" else 1.0)]),
                              fields[0].data[:, :, 0].ravel(order="F")[:, None], aux)
     assert rel(fields[0].data, fref[0]["data"]) < 1e-10
+
+
+@pytest.mark.parametrize("pol", ["TM", "TE"])
+def test_eigenfrequency_ring_matches_committed_fixture(fdfd, pol):
+    """same device and call as test_eigenfrequency_ring, compared with tests/golden/eig_ring.json (oracle values committed with
+    their generator, carrying the SURVEY 8c regression values at 400^2) instead of a live oracle run"""
+    import json
+    import os
+    z = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "eig_ring.json")))
+    ref = [complex(a, b) for a, b in z[f"{pol}_200"]]
+    d, _, _, _ = _ring(fdfd, 0.02)
+    om, _ = fdfd.eigenfrequency(d, fdfd.TM if pol == "TM" else fdfd.TE, 4, which="LM")
+    assert _match(om, ref) <= EIG_TOL
