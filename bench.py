@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--solver", default="bicgstab", choices=["bicgstab", "mlkrylov"],
                     help="sweep mode: bicgstab (default, the measured path) or the opt-in multilevel Krylov solver (csrc/mlkrylov.cu)")
     ap.add_argument("--ml-spec", default="6,12", help="--solver mlkrylov: FGMRES steps on levels 1,2[,3]")
-    ap.add_argument("--ml-restart", type=int, default=48, help="--solver mlkrylov: level-0 restart length")
+    ap.add_argument("--ml-restart", type=int, default=96, help="--solver mlkrylov: level-0 restart length")
     ap.add_argument("--mode", default="sweep", choices=["sweep", "slab"],
                     help="sweep (default, the metric): disjoint frequencies per GPU, weak scaling.  slab: ONE --grid^2 solve split "
                          "into row slabs over the GPUs (halo exchange + allreduce over NCCL), strong scaling (BASELINE config 5)")

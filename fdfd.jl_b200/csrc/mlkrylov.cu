@@ -266,12 +266,12 @@ int ml_setup(fdfd_problem* P, MLKrylov& M) {
   fdfd_ctx* ctx = P->ctx;
   Multigrid<float>* mg = P->mgf;
   M.P = P;
-  // spec: ml_spec bytes = k1 | k2 << 8 | k3 << 16 | restart << 24 ; 0 -> (6, 12, -, 48).  Levels beyond the hierarchy are dropped.
+  // spec: ml_spec bytes = k1 | k2 << 8 | k3 << 16 | restart << 24 ; 0 -> (6, 12, -, 96).  Levels beyond the hierarchy are dropped.
   uint32_t spec = (uint32_t)P->opts.ml_spec;
   if (const char* e = getenv("FDFD_ML_SPEC")) spec = (uint32_t)strtoul(e, nullptr, 0);   // diagnostics
   int ks[4] = {(int)(spec >> 24) & 0xff, (int)spec & 0xff, (int)(spec >> 8) & 0xff, (int)(spec >> 16) & 0xff};
   if ((spec & 0xffffff) == 0) { ks[1] = 6; ks[2] = 12; ks[3] = 0; }
-  if (ks[0] == 0) ks[0] = 48;
+  if (ks[0] == 0) ks[0] = 96;
   int nl = 1;
   while (nl < 4 && ks[nl] > 0 && nl < mg->levels()) ++nl;
   for (int l = 0; l < nl; ++l) ARG_CHECK(ctx, ks[l] >= 1 && ks[l] <= kMaxK, "multilevel Krylov: iteration counts must be in [1, 128]");
@@ -488,7 +488,7 @@ int krylov_multilevel(fdfd_problem* P, fdfd_info_t* info) {
   else {
     CUDA_TRY(ctx, cudaMemcpyAsync(r, b, N * sizeof(c128), cudaMemcpyDeviceToDevice, st));
     double rnorm = bnorm, prev_rel = 1.0;
-    int stalled = 0;
+    int stalled = 0, kcap = L.k;   // kcap: restart length, shrunk if the device cannot hold the whole basis
     while (true) {
       // ---- one FGMRES cycle from the current residual r (||r|| = rnorm)
       const c128 hb(rnorm, 0.0);
@@ -496,14 +496,20 @@ int krylov_multilevel(fdfd_problem* P, fdfd_info_t* info) {
       k_ml_scale_inv<<<L.nb, 256, 0, st>>>(N, L.sc.p, r, L.V[0].p); KLAUNCH(ctx);
       CUDA_TRY(ctx, cudaStreamSynchronize(st));   // hb is a local
       int j = 0;
-      for (; j < L.k && its < o.maxit; ) {
-        if (!L.Z[j].p) {   // grow the basis
-          MALLOC(L.Z[j], N);
+      for (; j < kcap && its < o.maxit; ) {
+        if (!L.Z[j].p || !L.V[j + 1].p) {   // grow the basis; out of memory = restart here with what there is
+          const bool ok = (L.Z[j].p || L.Z[j].alloc(N) == cudaSuccess) && (L.V[j + 1].p || L.V[j + 1].alloc(N) == cudaSuccess);
+          if (!ok) {
+            cudaGetLastError();
+            if (j == 0) { fdfd_set_error(ctx, "multilevel Krylov: out of device memory for the first basis vectors"); return FDFD_ERR_ALLOC; }
+            kcap = j;
+            if (o.verbose) fprintf(stderr, "[fdfd_b200] multilevel Krylov: basis capped at %d vectors by device memory\n", kcap);
+            break;
+          }
           const c128* zp = L.Z[j].p;
           CUDA_TRY(ctx, cudaMemcpyAsync(L.Zptr.p + j, &zp, sizeof(zp), cudaMemcpyHostToDevice, st));
           CUDA_TRY(ctx, cudaStreamSynchronize(st));   // zp is a local
         }
-        if (!L.V[j + 1].p) MALLOC(L.V[j + 1], N);
         FDFD_TRY(ml_arnoldi_step(M, 0, j));
         ++j; ++its;
         k_ml_lsq<<<1, 32, 0, st>>>(j, L.k + 1, L.H.p, L.sc.p, L.y.p, L.sc.p + 1, L.lsq.p, L.k); KLAUNCH(ctx);

@@ -91,7 +91,8 @@ typedef struct {
   int32_t use_graph;     /* replay the iteration as a CUDA graph (default 1) */
   int32_t concurrency;   /* fdfd_solve_driven: frequencies solved concurrently on separate streams (default 4) */
   int32_t ml_spec;       /* FDFD_SOLVER_MLKRYLOV: k1 | k2<<8 | k3<<16 | restart<<24 = FGMRES steps per solve on levels 1,2,3 (0 ends the
-                            list) and the level-0 restart length; 0 = defaults (6, 12; restart 48: 97 fine vectors = 26 GB at 4096^2) */
+                            list) and the level-0 restart length; 0 = defaults (6, 12; restart 96; the level-0 basis grows on demand, 2 vectors per iteration,
+                            and a full device forces an earlier restart instead of an error) */
 } fdfd_solve_opts_t;
 
 typedef struct {

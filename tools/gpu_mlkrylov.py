@@ -2,7 +2,7 @@
 BiCGSTAB + multigrid on the bench workload -- iterations, solve time, multigrid cycles per level.
 
     gpurun --timeout 900 -- 'python tools/gpu_mlkrylov.py 1024 2048 4096 > gpurun_out/mlkrylov.log 2>&1'
-    python tools/gpu_mlkrylov.py 4096 --spec 6,12 8,16 6,6,12 --restart 48        # spec sweep at one size
+    python tools/gpu_mlkrylov.py 4096 --spec 6,12 8,16 6,6,12 --restart 96        # spec sweep at one size
 """
 import argparse, ctypes as C, math, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -13,7 +13,7 @@ from fdfd_jl_b200 import _lib, workloads as wl
 ap = argparse.ArgumentParser()
 ap.add_argument("sizes", type=int, nargs="+")
 ap.add_argument("--spec", nargs="*", default=["6,12"], help="FGMRES steps on levels 1,2[,3], e.g. 6,12")
-ap.add_argument("--restart", type=int, default=48)
+ap.add_argument("--restart", type=int, default=96)
 ap.add_argument("--no-baseline", action="store_true")
 ap.add_argument("--maxit", type=int, default=6000)
 a = ap.parse_args()
