@@ -337,6 +337,51 @@ def _solve_modulated(d: ModulatedDevice, ctx=None, **kw):
     return out
 
 
+def _csc_arrays(A):
+    """(n, colptr, rowval, nzval) of a square SciPy sparse matrix / (colptr, rowval, nzval) triple, Int64 / ComplexF64, 0-based."""
+    if isinstance(A, tuple):
+        colptr, rowval, nzval = A
+        n = len(colptr) - 1
+    else:
+        A = A.tocsc()
+        if A.shape[0] != A.shape[1]:
+            raise ValueError("dolinearsolve needs a square matrix")
+        n, colptr, rowval, nzval = A.shape[0], A.indptr, A.indices, A.data
+    return (n, np.ascontiguousarray(colptr, dtype=np.int64), np.ascontiguousarray(rowval, dtype=np.int64),
+            np.ascontiguousarray(nzval, dtype=np.complex128))
+
+
+def dolinearsolve(A, b, matrixsym=None, index_base=0, ctx: Context = None, return_info=False, **kw):
+    """dolinearsolve(A::SparseMatrixCSC, b, matrixsym) -> x (src/solver/solver.jl:4-41) for callers that assemble their own matrix
+    (nonlinear.jl:69,97,120; eigen.jl:32-66).  A: SciPy sparse matrix or a (colptr, rowval, nzval) CSC triple with the given
+    index_base; `matrixsym` is accepted and ignored, as in the reference (solver.jl:29).  BiCGSTAB + Jacobi on the GPU
+    (fdfd_dolinearsolve_csc); options: tol, maxit, check_every, use_graph, verbose."""
+    n, colptr, rowval, nzval = _csc_arrays(A)
+    bb = np.ascontiguousarray(np.asarray(b, dtype=np.complex128).ravel(order="F"))
+    if bb.size != n:
+        raise ValueError(f"b has {bb.size} entries, A is {n} x {n}")
+    ctx = ctx or default_context()
+    o = _opts(kw)
+    x = np.empty(n, dtype=np.complex128)
+    info = Info()
+    code = lib().fdfd_dolinearsolve_csc(ctx.handle, n, ptr(colptr), ptr(rowval), ptr(nzval), int(index_base), ptr(bb), C.byref(o),
+                                        ptr(x), C.byref(info))
+    check(code, ctx.handle)
+    return (x, info.asdict()) if return_info else x
+
+
+def _sell_spmv_host(A, x, index_base=0):
+    """host-only test hook: y = A x through the library's CSC -> SELL-32 transposition (no GPU) -> (y, dinv, padded_entries)"""
+    n, colptr, rowval, nzval = _csc_arrays(A)
+    xx = np.ascontiguousarray(x, dtype=np.complex128)
+    y = np.empty(n, dtype=np.complex128); dinv = np.empty(n, dtype=np.complex128)
+    pad = C.c_int64(0)
+    code = lib().fdfd_debug_sell_spmv(n, ptr(colptr), ptr(rowval), ptr(nzval), int(index_base), ptr(xx), ptr(y), ptr(dinv), C.byref(pad))
+    if code != 0:
+        raise FdfdError(code, "fdfd_debug_sell_spmv: bad CSC arrays")
+    return y, dinv, pad.value
+
+
 def eigenfrequency(d: Device, pol, nev, which="LM", ncv=0, ctx: Context = None, **kw):
     """eigenfrequency(d, pol, neigenvalues; which=:LM) (src/solver/eigen.jl:69-115) -> (ω, fields)."""
     ctx = ctx or default_context()

@@ -1,0 +1,245 @@
+// linsolve.cu -- dolinearsolve-level entry (SURVEY §8b "optional dolinearsolve-level export taking CSC", §8f row 4):
+// x = A^-1 b for an ASSEMBLED SparseMatrixCSC handed over by the caller, for the reference call sites that build their own
+// matrix and only use the solver seam -- dolinearsolve(A, b, matrixsym) in src/solver/solver.jl:4-41, called from
+// src/solver/nonlinear.jl:69,97,120 (chi-3 outer loops) and usable by src/solver/eigen.jl:32-66.
+//
+// Not the headline path: the driven / modulated / eigenfrequency entry points are matrix-free and multigrid-preconditioned.
+// A general sparse matrix carries no grid, so this path is the operator-agnostic BiCGSTAB of krylov.cu with
+//   * apply  = SpMV over a SELL-32 layout (sliced ELLPACK, slice = one warp of rows, entries of a slice stored k-major so
+//     that the 32 lanes of a warp read 32 consecutive values / column indices: HBM-coalesced without a segmented reduction;
+//     int32 column indices; algorithmic bytes per stored entry 16 + 4, plus 16 B/row for y, 16 B/row gathered x from L2),
+//     the Krylov dot products fused into the SpMV exactly like in k_apply (stencil.cu),
+//   * precond = diagonal (Jacobi) scaling in fp64.
+// The CSC -> SELL transposition is host work inside the call (the caller's arrays are host arrays; O(nnz), one pass to count,
+// one to scatter) and its arithmetic core is shared with the host-only test hook fdfd_debug_sell_spmv.
+//
+// STATUS: written in a session without GPU access -- compiles for sm_100a, exercised on hardware by tests/unverified/ only;
+// the host transposition / SELL indexing is checked on the CPU (tests/test_cabi_cpu.py).
+#include "krylov.cuh"
+#include "reduce.cuh"
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+
+namespace {
+
+constexpr int kSlice = 32;       // rows per slice = lanes per warp
+constexpr int kSpThreads = 256;  // 8 slices per CTA
+
+// host-side SELL-32 image of a CSC matrix
+struct SellHost {
+  int64_t n = 0, nslices = 0;
+  std::vector<int64_t> sptr;     // nslices + 1: first entry of slice s (entries of a slice: width_s * 32, k-major)
+  std::vector<int32_t> col;      // padded entries point at the row itself with value 0
+  std::vector<c128> val;
+  std::vector<c128> dinv;        // 1 / A[i,i]  (1 where the diagonal is absent or zero)
+  int64_t nnz = 0;
+};
+
+// CSC (colptr n+1, rowval, nzval; indices with the given base; duplicates are summed like Julia's sparse(I,J,V)) -> SELL-32
+int csc_to_sell(int64_t n, const int64_t* colptr, const int64_t* rowval, const fdfd_c128* nzval, int base, SellHost& S, std::string& err) {
+  S.n = n; S.nslices = (n + kSlice - 1) / kSlice;
+  if (colptr[0] != base) { err = "colptr[0] does not equal the index base"; return FDFD_ERR_ARG; }
+  const int64_t nnz = colptr[n] - base;
+  if (nnz < 0) { err = "colptr is not non-decreasing"; return FDFD_ERR_ARG; }
+  S.nnz = nnz;
+  std::vector<int32_t> cnt(n, 0);
+  for (int64_t j = 0; j < n; ++j) {
+    if (colptr[j + 1] < colptr[j]) { err = "colptr is not non-decreasing"; return FDFD_ERR_ARG; }
+    for (int64_t e = colptr[j] - base; e < colptr[j + 1] - base; ++e) {
+      const int64_t i = rowval[e] - base;
+      if (i < 0 || i >= n) { err = "rowval out of range"; return FDFD_ERR_ARG; }
+      ++cnt[i];
+    }
+  }
+  S.sptr.assign(S.nslices + 1, 0);
+  for (int64_t s = 0; s < S.nslices; ++s) {
+    int32_t w = 0;
+    for (int64_t i = s * kSlice; i < std::min(n, (s + 1) * kSlice); ++i) w = std::max(w, cnt[i]);
+    S.sptr[s + 1] = S.sptr[s] + (int64_t)w * kSlice;
+  }
+  const int64_t cap = S.sptr[S.nslices];
+  S.col.resize(cap); S.val.assign(cap, c128(0.0, 0.0));
+  for (int64_t s = 0; s < S.nslices; ++s)     // padding: gather the row's own x (always in range; rows past n gather x[n-1]) times 0
+    for (int64_t e = S.sptr[s]; e < S.sptr[s + 1]; ++e) S.col[e] = (int32_t)std::min(n - 1, s * kSlice + (e - S.sptr[s]) % kSlice);
+  std::vector<c128> diag(n, c128(0.0, 0.0));
+  std::fill(cnt.begin(), cnt.end(), 0);
+  for (int64_t j = 0; j < n; ++j)             // columns ascending => every row's entries end up sorted by column
+    for (int64_t e = colptr[j] - base; e < colptr[j + 1] - base; ++e) {
+      const int64_t i = rowval[e] - base;
+      const c128 v(nzval[e].re, nzval[e].im);
+      const int64_t s = i / kSlice, r = i % kSlice;
+      const int64_t at = S.sptr[s] + (int64_t)cnt[i] * kSlice + r;
+      S.col[at] = (int32_t)j; S.val[at] = v;
+      ++cnt[i];
+      if (i == j) diag[i] += v;
+    }
+  S.dinv.resize(n);
+  for (int64_t i = 0; i < n; ++i) S.dinv[i] = norm2(diag[i]) > 0.0 ? crecip(diag[i]) : c128(1.0, 0.0);
+  return FDFD_OK;
+}
+
+// one row of y = A x in the SELL layout (shared by the kernel and the host test hook: same order of summation)
+__host__ __device__ __forceinline__ c128 sell_row(int64_t lo, int64_t hi, int r, const int32_t* __restrict__ col, const c128* __restrict__ val,
+                                                  const c128* __restrict__ x) {
+  c128 acc(0.0, 0.0);
+  for (int64_t e = lo + r; e < hi; e += kSlice) cfma(acc, val[e], x[col[e]]);
+  return acc;
+}
+
+// y = A x, one lane per row, one warp per slice (grid-stride over slices); fused dots as in k_apply:
+//   NDOT 1: partials[block] = <d0, y>;  NDOT 2: partials[block] = (<y, d0>, |y|^2, 0)
+template <int NDOT>
+__global__ void __launch_bounds__(kSpThreads) k_sell_spmv(int64_t n, int64_t nslices, const int64_t* __restrict__ sptr, const int32_t* __restrict__ col,
+                                                          const c128* __restrict__ val, const c128* __restrict__ x, c128* __restrict__ y,
+                                                          const c128* __restrict__ d0, c128* __restrict__ partials, const int* __restrict__ done) {
+  if (done && *done) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t wpb = kSpThreads / 32;
+  double acc[NDOT > 0 ? 2 * NDOT : 1];
+#pragma unroll
+  for (int k = 0; k < (NDOT > 0 ? 2 * NDOT : 1); ++k) acc[k] = 0.0;
+  for (int64_t s = blockIdx.x * wpb + (threadIdx.x >> 5); s < nslices; s += (int64_t)gridDim.x * wpb) {
+    const int64_t i = s * kSlice + lane;
+    const c128 out = sell_row(sptr[s], sptr[s + 1], lane, col, val, x);
+    if (i < n) {
+      y[i] = out;
+      if constexpr (NDOT == 1) {
+        const c128 p = cmulc(d0[i], out);
+        acc[0] += p.x; acc[1] += p.y;
+      } else if constexpr (NDOT == 2) {
+        const c128 p = cmulc(out, d0[i]);
+        acc[0] += p.x; acc[1] += p.y;
+        acc[2] += norm2(out);
+      }
+    }
+  }
+  if constexpr (NDOT > 0) block_reduce_store<kSpThreads, 2 * NDOT>(acc, reinterpret_cast<double*>(partials) + (size_t)blockIdx.x * 2 * NDOT);
+}
+
+// out = dinv .* in   (skipped once the solver's convergence flag is up, like every kernel of a captured iteration)
+__global__ void k_diag_scale(int64_t n, const c128* __restrict__ dinv, const c128* __restrict__ in, c128* __restrict__ out, const int* __restrict__ done) {
+  if (done && *done) return;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = dinv[i] * in[i];
+}
+
+struct SellDev {
+  int64_t n = 0, nslices = 0;
+  int blocks = 0;
+  DevBuf<int64_t> sptr;
+  DevBuf<int32_t> col;
+  DevBuf<c128> val, dinv;
+};
+
+int sell_upload(fdfd_ctx* ctx, const SellHost& H, SellDev& D) {
+  D.n = H.n; D.nslices = H.nslices;
+  const int64_t wpb = kSpThreads / 32;
+  D.blocks = (int)std::max<int64_t>(1, std::min<int64_t>((H.nslices + wpb - 1) / wpb, (int64_t)ctx->num_sms * 8));
+  CUDA_TRY(ctx, D.sptr.alloc(H.sptr.size())); CUDA_TRY(ctx, D.col.alloc(std::max<size_t>(1, H.col.size())));
+  CUDA_TRY(ctx, D.val.alloc(std::max<size_t>(1, H.val.size()))); CUDA_TRY(ctx, D.dinv.alloc(H.n));
+  CUDA_TRY(ctx, cudaMemcpyAsync(D.sptr.p, H.sptr.data(), H.sptr.size() * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+  if (!H.col.empty()) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(D.col.p, H.col.data(), H.col.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(D.val.p, H.val.data(), H.val.size() * sizeof(c128), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CUDA_TRY(ctx, cudaMemcpyAsync(D.dinv.p, H.dinv.data(), H.n * sizeof(c128), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // H may go out of scope
+  return FDFD_OK;
+}
+
+int sell_apply(fdfd_ctx* ctx, const SellDev& D, const c128* x, c128* y, const DotSpec& ds) {
+  cudaStream_t st = ctx->stream;
+#define SPMV(ND) k_sell_spmv<ND><<<D.blocks, kSpThreads, 0, st>>>(D.n, D.nslices, D.sptr.p, D.col.p, D.val.p, x, y, ds.d0, ds.partials, ds.done)
+  switch (ds.ndot) {
+    case 0: SPMV(0); break;
+    case 1: SPMV(1); break;
+    case 2: SPMV(2); break;
+    default: fdfd_set_error(ctx, "sell_apply: ndot must be 0, 1 or 2"); return FDFD_ERR_ARG;
+  }
+#undef SPMV
+  KLAUNCH(ctx);
+  if (ds.nblocks_out) *ds.nblocks_out = D.blocks;
+  return FDFD_OK;
+}
+
+}  // namespace
+
+// dolinearsolve(A::SparseMatrixCSC{ComplexF64,Int64}, b, matrixsym) -> x   (src/solver/solver.jl:4-41; matrixsym is ignored there too, :29).
+// colptr / rowval / nzval are HOST arrays exactly as Julia stores them (A.colptr, A.rowval, A.nzval; index_base 1) or 0-based;
+// b and x may be host or device pointers.  Solver: BiCGSTAB + Jacobi on the SELL-32 image of A; opts->tol / maxit / check_every /
+// use_graph / verbose are honoured, the preconditioner choice is not (a matrix has no grid to build a multigrid hierarchy from).
+extern "C" int fdfd_dolinearsolve_csc(fdfd_ctx* ctx, int64_t n, const int64_t* colptr, const int64_t* rowval, const fdfd_c128* nzval,
+                                      int index_base, const fdfd_c128* b, const fdfd_solve_opts_t* opts, fdfd_c128* x, fdfd_info_t* info) {
+  ARG_CHECK(ctx, ctx != nullptr, "ctx is NULL");
+  ARG_CHECK(ctx, n >= 1 && n < ((int64_t)1 << 31), "n must be in [1, 2^31)");
+  ARG_CHECK(ctx, colptr && rowval && nzval && b && x, "NULL argument");
+  ARG_CHECK(ctx, index_base == 0 || index_base == 1, "index_base must be 0 or 1");
+  using clk = std::chrono::steady_clock;
+  const auto t0 = clk::now();
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  fdfd_solve_opts_t o;
+  if (opts) o = *opts; else fdfd_default_opts(&o);
+  o.solver = FDFD_SOLVER_BICGSTAB; o.precond = FDFD_PRECOND_JACOBI;
+  SellDev D;
+  {
+    SellHost H;
+    std::string err;
+    const int st = csc_to_sell(n, colptr, rowval, nzval, index_base, H, err);
+    if (st != FDFD_OK) { fdfd_set_error(ctx, "fdfd_dolinearsolve_csc: %s", err.c_str()); return st; }
+    FDFD_TRY(sell_upload(ctx, H, D));
+  }
+  KrylovWork W;
+  FDFD_TRY(W.alloc(ctx, n, D.blocks, o.maxit, true));
+  FDFD_TRY(fdfd_copy_in(ctx, W.b.p, b, (size_t)n * sizeof(c128)));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  const double setup_ms = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+
+  KrylovOps k;
+  k.prec_f32 = false; k.prec_rhs = nullptr; k.fscale = 1.0;
+  k.nab = D.blocks;
+  k.apply = [ctx, &D](const void* xin, bool x_f32, c128* y, const DotSpec& ds) -> int {
+    if (x_f32) { fdfd_set_error(ctx, "fdfd_dolinearsolve_csc: internal: fp32 input to the fp64 SpMV"); return FDFD_ERR_ARG; }
+    return sell_apply(ctx, D, (const c128*)xin, y, ds);
+  };
+  k.precond = [ctx, &D, &W](bool hold, const void** out) -> int {
+    c128* dst = hold ? W.ph.p : W.sh.p;
+    *out = dst;
+    k_diag_scale<<<W.nvec_blocks, 256, 0, ctx->stream>>>(D.n, D.dinv.p, hold ? W.p.p : W.s.p, dst, &W.scal.p->done); KLAUNCH(ctx);
+    return FDFD_OK;
+  };
+  fdfd_info_t inf{};
+  FDFD_TRY(krylov_bicgstab(ctx, W, k, o, &inf));
+  inf.setup_ms = setup_ms;
+  inf.mg_levels = 0;
+  FDFD_TRY(fdfd_copy_out(ctx, x, W.x.p, (size_t)n * sizeof(c128)));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  inf.total_ms = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+  if (info) *info = inf;
+  if (inf.flag != FDFD_OK) {
+    fdfd_set_error(ctx, "fdfd_dolinearsolve_csc: Krylov solver stopped with flag %d after %d iterations, relres %.3e", inf.flag, inf.iters, inf.relres);
+    return inf.flag;
+  }
+  return FDFD_OK;
+}
+
+// host-only test hook (no GPU needed): y = A x through the SAME CSC -> SELL-32 transposition and the same per-row summation as the
+// kernel; also returns the padded entry count and the inverse diagonal the Jacobi preconditioner would use
+extern "C" int fdfd_debug_sell_spmv(int64_t n, const int64_t* colptr, const int64_t* rowval, const fdfd_c128* nzval, int index_base,
+                                    const fdfd_c128* x, fdfd_c128* y, fdfd_c128* dinv, int64_t* padded_entries) {
+  if (n < 1 || n >= ((int64_t)1 << 31) || !colptr || !rowval || !nzval || !x || !y || !(index_base == 0 || index_base == 1)) return FDFD_ERR_ARG;
+  SellHost H;
+  std::string err;
+  const int st = csc_to_sell(n, colptr, rowval, nzval, index_base, H, err);
+  if (st != FDFD_OK) return st;
+  const c128* xx = reinterpret_cast<const c128*>(x);
+  c128* yy = reinterpret_cast<c128*>(y);
+  for (int64_t s = 0; s < H.nslices; ++s)
+    for (int r = 0; r < kSlice; ++r) {
+      const int64_t i = s * kSlice + r;
+      const c128 out = sell_row(H.sptr[s], H.sptr[s + 1], r, H.col.data(), H.val.data(), xx);
+      if (i < n) yy[i] = out;
+    }
+  if (dinv) std::memcpy(dinv, H.dinv.data(), sizeof(c128) * n);
+  if (padded_entries) *padded_entries = H.sptr[H.nslices];
+  return FDFD_OK;
+}

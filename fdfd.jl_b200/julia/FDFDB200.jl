@@ -161,4 +161,21 @@ function eigenfrequency_slab_b200(d::AbstractDevice{2}, nev::Int, comm::Ptr{Cvoi
     return (ω, out)
 end
 
+# ---- the reference's own seam: dolinearsolve(A, b, matrixsym) (src/solver/solver.jl:4-41) for callers that assemble their own
+# matrix -- the chi-3 outer loops (nonlinear.jl:69,97,120) and the 2-D eigenmode (eigen.jl:32-66).  In solver.jl the maintainer
+# adds one branch next to the "pardiso" one (:19):   elseif solver == "b200"; x = FDFDB200.dolinearsolve_b200(A, b)
+# BiCGSTAB + Jacobi on a SELL-32 image of A (csrc/linsolve.cu): a compatibility path; the L3 entry points above are the fast ones.
+using SparseArrays: SparseMatrixCSC
+function dolinearsolve_b200(A::SparseMatrixCSC, b::AbstractVector; tol::Float64=1e-10, maxit::Int=100000)
+    n = size(A, 1); n == size(A, 2) == length(b) || error("dolinearsolve_b200: dimension mismatch")
+    colptr = Vector{Int64}(A.colptr); rowval = Vector{Int64}(A.rowval); nzval = Vector{ComplexF64}(A.nzval)
+    bb = Vector{ComplexF64}(b); x = Vector{ComplexF64}(undef, n)
+    opts = COpts(); opts.tol = tol; opts.maxit = maxit; info = CInfo()
+    GC.@preserve colptr rowval nzval bb x check(ccall((:fdfd_dolinearsolve_csc, LIB), Cint,
+        (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{ComplexF64}, Cint, Ptr{ComplexF64}, Ref{COpts}, Ptr{ComplexF64}, Ref{CInfo}),
+        ctx(), n, colptr, rowval, nzval, 1, bb, opts, x, info))
+    @info "fdfd_b200 dolinearsolve: $(info.iters) iterations, relres $(info.relres), $(info.total_ms) ms"
+    return x
+end
+
 end # module

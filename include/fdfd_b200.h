@@ -257,6 +257,19 @@ int fdfd_eigenfrequency_slab(fdfd_ctx* ctx, fdfd_comm* comm, const fdfd_grid_t* 
 /* counters of the communicator since creation: exchanges, allreduces, bytes sent by this rank */
 int fdfd_comm_stats(fdfd_comm* comm, int64_t* n_exchange, int64_t* n_allreduce, int64_t* bytes_sent);
 
+/* ---- dolinearsolve-level entry.  Replaces dolinearsolve(A::SparseMatrixCSC, b, matrixsym) -> x (src/solver/solver.jl:4-41)
+ * for callers that assemble their own matrix and only use the solver seam: the chi-3 outer loops (src/solver/nonlinear.jl:69,97,120)
+ * and the 2-D eigenmode (src/solver/eigen.jl:32-66).  colptr (n+1), rowval, nzval are HOST arrays as Julia stores them
+ * (A.colptr, A.rowval, A.nzval with index_base 1; 0 for C callers); duplicates are summed; b, x (n) host or device.
+ * Solver: BiCGSTAB + Jacobi over a SELL-32 image of A (a matrix carries no grid, so no multigrid): a compatibility path, the
+ * driven / modulated / eigenfrequency entry points above are the fast ones.  opts: tol, maxit, check_every, use_graph, verbose. */
+int fdfd_dolinearsolve_csc(fdfd_ctx* ctx, int64_t n, const int64_t* colptr, const int64_t* rowval, const fdfd_c128* nzval,
+                           int index_base, const fdfd_c128* b, const fdfd_solve_opts_t* opts, fdfd_c128* x, fdfd_info_t* info);
+/* host-only test hook (no GPU needed): y = A x through the same CSC -> SELL-32 transposition and per-row summation order as the
+ * SpMV kernel; dinv (n, optional) = the Jacobi preconditioner's inverse diagonal; padded_entries (optional) = stored entries. */
+int fdfd_debug_sell_spmv(int64_t n, const int64_t* colptr, const int64_t* rowval, const fdfd_c128* nzval, int index_base,
+                         const fdfd_c128* x, fdfd_c128* y, fdfd_c128* dinv, int64_t* padded_entries);
+
 /* host-only test hook (no GPU needed): the small dense complex Hessenberg eigen-solver behind the Ritz pairs of
  * fdfd_eigenfrequency.  H, evecs: column-major n x n; evals: n. */
 int fdfd_debug_hess_eig(int n, const fdfd_c128* H, fdfd_c128* evals, fdfd_c128* evecs);

@@ -128,3 +128,57 @@ def test_mlkrylov_transfers_host(fdfd):
         if nx % 2 == 0 and ny % 2 == 0:
             ones_f = np.asfortranarray(np.ones((nx, ny), complex))
             assert L.fdfd_debug_ml_transfer(nx, ny, 0, 0.25, ptr(ones_f), ptr(zt)) == 0 and np.abs(zt - 1).max() < 1e-15
+
+
+def test_dolinearsolve_sell_transposition_host(fdfd):
+    """fdfd_dolinearsolve_csc's host half (solver.jl:4 seam): the CSC -> SELL-32 transposition and the per-row summation the SpMV
+    kernel shares with this hook reproduce A @ x and 1/diag(A) for ragged, empty-row, duplicate-entry and n % 32 != 0 matrices in
+    both index bases, and for the reference's own TM system matrix (oracle assembly, driven.jl:35); malformed CSC is refused."""
+    import numpy as np
+    import scipy.sparse as sp
+    from oracle import fdfd_oracle as O
+    rng = np.random.default_rng(7)
+    for n, dens in ((1, 1.0), (5, 0.5), (32, 0.2), (33, 0.1), (257, 0.02), (1000, 0.006)):
+        A = (sp.random(n, n, density=dens, random_state=rng) + 1j * sp.random(n, n, density=dens, random_state=rng)).tocsc()
+        if n > 5:   # a diagonal with some exact zeros, and rows left empty by the random pattern
+            A = (A + sp.diags((rng.standard_normal(n) + 1j * rng.standard_normal(n)) * (rng.random(n) > 0.3))).tocsc()
+        A.sort_indices()
+        x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        d = A.diagonal()
+        dref = np.where(d != 0, 1 / np.where(d != 0, d, 1), 1)
+        for base in (0, 1):
+            y, dinv, pad = fdfd._sell_spmv_host((A.indptr + base, A.indices + base, A.data), x, index_base=base)
+            assert np.abs(y - A @ x).max() <= 1e-13 * max(1.0, np.abs(A @ x).max())
+            assert np.abs(dinv * np.where(d != 0, d, 1) - 1).max() <= 1e-12 and np.all(dinv[d == 0] == 1)
+            assert pad % 32 == 0 and pad >= A.nnz
+            assert np.allclose(dinv, dref, rtol=1e-12)
+    # duplicates are summed (Julia's sparse(I, J, V) semantics)
+    colptr, rowval = np.array([0, 2, 3]), np.array([0, 0, 1])
+    y, dinv, _ = fdfd._sell_spmv_host((colptr, rowval, np.array([1 + 1j, 2.0, 4.0])), np.array([1.0, 1.0]))
+    assert np.allclose(y, [3 + 1j, 4.0]) and np.allclose(dinv, [1 / (3 + 1j), 0.25])
+    # the reference's TM matrix (5 nnz/row, periodic wrap entries): SELL padding is zero when every row has the same length
+    g = O.Grid2D(0.05, [6, 5], [0.0, 2.0], [-0.8, 0.8])
+    dev = O.Device(g, [2 * np.pi * 200e12])
+    dev.eps_r[10:20, 12:18] = 12.0
+    A = O.system_matrix(dev, dev.omega[0], O.TM)[0].tocsc()
+    A.sort_indices()
+    x = rng.standard_normal(A.shape[0]) + 1j * rng.standard_normal(A.shape[0])
+    y, _, pad = fdfd._sell_spmv_host(A, x)
+    assert np.abs(y - A @ x).max() <= 1e-13 * np.abs(A @ x).max() and pad == 5 * A.shape[0]
+    with pytest.raises(fdfd.FdfdError):
+        fdfd._sell_spmv_host((np.array([0, 1, 2]), np.array([0, 5]), np.array([1.0, 1.0])), np.ones(2))
+    with pytest.raises(fdfd.FdfdError):
+        fdfd._sell_spmv_host((np.array([0, 2, 1]), np.array([0, 1]), np.array([1.0, 1.0])), np.ones(2))
+
+
+def test_dolinearsolve_fails_loudly_without_gpu(fdfd):
+    import numpy as np
+    import scipy.sparse as sp
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(fdfd.FdfdError) as e:
+        fdfd.dolinearsolve(sp.identity(4, dtype=complex, format="csc"), np.ones(4))
+    assert "no CPU path" in str(e.value)
+    with pytest.raises(ValueError):
+        fdfd.dolinearsolve(sp.random(3, 4, density=0.5, format="csc"), np.ones(4))
