@@ -351,11 +351,14 @@ def _csc_arrays(A):
             np.ascontiguousarray(nzval, dtype=np.complex128))
 
 
-def dolinearsolve(A, b, matrixsym=None, index_base=0, ctx: Context = None, return_info=False, **kw):
+def dolinearsolve(A, b, matrixsym=None, index_base=0, grid: Grid = None, omega=None, ctx: Context = None, return_info=False, **kw):
     """dolinearsolve(A::SparseMatrixCSC, b, matrixsym) -> x (src/solver/solver.jl:4-41) for callers that assemble their own matrix
     (nonlinear.jl:69,97,120; eigen.jl:32-66).  A: SciPy sparse matrix or a (colptr, rowval, nzval) CSC triple with the given
     index_base; `matrixsym` is accepted and ignored, as in the reference (solver.jl:29).  BiCGSTAB + Jacobi on the GPU
-    (fdfd_dolinearsolve_csc); options: tol, maxit, check_every, use_graph, verbose."""
+    (fdfd_dolinearsolve_csc); options: tol, maxit, check_every, use_graph, verbose.  With `grid` and `omega` (the grid A was
+    assembled on) the library checks whether A is the TM operator of that grid for some permittivity -- the first solve and the
+    Born steps of nonlinear.jl are -- and then runs the multigrid-preconditioned solver (fdfd_dolinearsolve_csc_grid;
+    info["mg_levels"] > 0), else the generic path."""
     n, colptr, rowval, nzval = _csc_arrays(A)
     bb = np.ascontiguousarray(np.asarray(b, dtype=np.complex128).ravel(order="F"))
     if bb.size != n:
@@ -364,19 +367,28 @@ def dolinearsolve(A, b, matrixsym=None, index_base=0, ctx: Context = None, retur
     o = _opts(kw)
     x = np.empty(n, dtype=np.complex128)
     info = Info()
-    code = lib().fdfd_dolinearsolve_csc(ctx.handle, n, ptr(colptr), ptr(rowval), ptr(nzval), int(index_base), ptr(bb), C.byref(o),
-                                        ptr(x), C.byref(info))
+    if grid is not None:
+        if omega is None:
+            raise ValueError("dolinearsolve: grid given without omega")
+        gc = grid.as_c()
+        code = lib().fdfd_dolinearsolve_csc_grid(ctx.handle, C.byref(gc), float(omega), n, ptr(colptr), ptr(rowval), ptr(nzval),
+                                                 int(index_base), ptr(bb), C.byref(o), ptr(x), C.byref(info))
+    else:
+        code = lib().fdfd_dolinearsolve_csc(ctx.handle, n, ptr(colptr), ptr(rowval), ptr(nzval), int(index_base), ptr(bb), C.byref(o),
+                                            ptr(x), C.byref(info))
     check(code, ctx.handle)
     return (x, info.asdict()) if return_info else x
 
 
-def _sell_spmv_host(A, x, index_base=0):
-    """host-only test hook: y = A x through the library's CSC -> SELL-32 transposition (no GPU) -> (y, dinv, padded_entries)"""
+def _sell_spmv_host(A, x, index_base=0, rowsum=None):
+    """host-only test hook: y = A x through the library's CSC -> SELL-32 transposition (no GPU) -> (y, dinv, padded_entries);
+    rowsum: optional complex128 (n) output array receiving A 1"""
     n, colptr, rowval, nzval = _csc_arrays(A)
     xx = np.ascontiguousarray(x, dtype=np.complex128)
     y = np.empty(n, dtype=np.complex128); dinv = np.empty(n, dtype=np.complex128)
     pad = C.c_int64(0)
-    code = lib().fdfd_debug_sell_spmv(n, ptr(colptr), ptr(rowval), ptr(nzval), int(index_base), ptr(xx), ptr(y), ptr(dinv), C.byref(pad))
+    rs = None if rowsum is None else rowsum
+    code = lib().fdfd_debug_sell_spmv(n, ptr(colptr), ptr(rowval), ptr(nzval), int(index_base), ptr(xx), ptr(y), ptr(dinv), ptr(rs), C.byref(pad))
     if code != 0:
         raise FdfdError(code, "fdfd_debug_sell_spmv: bad CSC arrays")
     return y, dinv, pad.value

@@ -33,6 +33,7 @@ struct SellHost {
   std::vector<int32_t> col;      // padded entries point at the row itself with value 0
   std::vector<c128> val;
   std::vector<c128> dinv;        // 1 / A[i,i]  (1 where the diagonal is absent or zero)
+  std::vector<c128> rowsum;      // sum_j A[i,j] = (A 1)[i]: the mass term of a difference stencil (grid-hinted path)
   int64_t nnz = 0;
 };
 
@@ -63,6 +64,7 @@ int csc_to_sell(int64_t n, const int64_t* colptr, const int64_t* rowval, const f
   for (int64_t s = 0; s < S.nslices; ++s)     // padding: gather the row's own x (always in range; rows past n gather x[n-1]) times 0
     for (int64_t e = S.sptr[s]; e < S.sptr[s + 1]; ++e) S.col[e] = (int32_t)std::min(n - 1, s * kSlice + (e - S.sptr[s]) % kSlice);
   std::vector<c128> diag(n, c128(0.0, 0.0));
+  S.rowsum.assign(n, c128(0.0, 0.0));
   std::fill(cnt.begin(), cnt.end(), 0);
   for (int64_t j = 0; j < n; ++j)             // columns ascending => every row's entries end up sorted by column
     for (int64_t e = colptr[j] - base; e < colptr[j + 1] - base; ++e) {
@@ -73,6 +75,7 @@ int csc_to_sell(int64_t n, const int64_t* colptr, const int64_t* rowval, const f
       S.col[at] = (int32_t)j; S.val[at] = v;
       ++cnt[i];
       if (i == j) diag[i] += v;
+      S.rowsum[i] += v;
     }
   S.dinv.resize(n);
   for (int64_t i = 0; i < n; ++i) S.dinv[i] = norm2(diag[i]) > 0.0 ? crecip(diag[i]) : c128(1.0, 0.0);
@@ -123,6 +126,24 @@ __global__ void k_diag_scale(int64_t n, const c128* __restrict__ dinv, const c12
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = dinv[i] * in[i];
 }
 
+// deterministic test vector with O(1) entries of both signs in both parts (operator comparison of the grid-hinted path)
+__global__ void k_probe_fill(int64_t n, c128* __restrict__ v) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t h = (uint64_t)i * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
+    h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32;
+    v[i] = c128((double)(h & 0xffffff) / 8388608.0 - 1.0, (double)((h >> 24) & 0xffffff) / 8388608.0 - 1.0);
+  }
+}
+// partials[block] = (|a - b|^2, |a|^2)
+__global__ void __launch_bounds__(kSpThreads) k_diff_norms(int64_t n, const c128* __restrict__ a, const c128* __restrict__ b, double* __restrict__ partials) {
+  double acc[2] = {0.0, 0.0};
+  for (int64_t i = blockIdx.x * (int64_t)kSpThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kSpThreads) {
+    const c128 ai = a[i];
+    acc[0] += norm2(ai - b[i]); acc[1] += norm2(ai);
+  }
+  block_reduce_store<kSpThreads, 2>(acc, partials + (size_t)blockIdx.x * 2);
+}
+
 struct SellDev {
   int64_t n = 0, nslices = 0;
   int blocks = 0;
@@ -164,36 +185,20 @@ int sell_apply(fdfd_ctx* ctx, const SellDev& D, const c128* x, c128* y, const Do
 
 }  // namespace
 
-// dolinearsolve(A::SparseMatrixCSC{ComplexF64,Int64}, b, matrixsym) -> x   (src/solver/solver.jl:4-41; matrixsym is ignored there too, :29).
-// colptr / rowval / nzval are HOST arrays exactly as Julia stores them (A.colptr, A.rowval, A.nzval; index_base 1) or 0-based;
-// b and x may be host or device pointers.  Solver: BiCGSTAB + Jacobi on the SELL-32 image of A; opts->tol / maxit / check_every /
-// use_graph / verbose are honoured, the preconditioner choice is not (a matrix has no grid to build a multigrid hierarchy from).
-extern "C" int fdfd_dolinearsolve_csc(fdfd_ctx* ctx, int64_t n, const int64_t* colptr, const int64_t* rowval, const fdfd_c128* nzval,
-                                      int index_base, const fdfd_c128* b, const fdfd_solve_opts_t* opts, fdfd_c128* x, fdfd_info_t* info) {
-  ARG_CHECK(ctx, ctx != nullptr, "ctx is NULL");
-  ARG_CHECK(ctx, n >= 1 && n < ((int64_t)1 << 31), "n must be in [1, 2^31)");
-  ARG_CHECK(ctx, colptr && rowval && nzval && b && x, "NULL argument");
-  ARG_CHECK(ctx, index_base == 0 || index_base == 1, "index_base must be 0 or 1");
-  using clk = std::chrono::steady_clock;
-  const auto t0 = clk::now();
-  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  fdfd_solve_opts_t o;
-  if (opts) o = *opts; else fdfd_default_opts(&o);
+namespace {
+
+using clk = std::chrono::steady_clock;
+double ms_since(clk::time_point t0) { return std::chrono::duration<double, std::milli>(clk::now() - t0).count(); }
+
+// BiCGSTAB + Jacobi on the SELL image (the path of a matrix without a grid)
+int solve_generic(fdfd_ctx* ctx, const SellDev& D, const fdfd_c128* b, fdfd_solve_opts_t o, fdfd_c128* x, fdfd_info_t* info, clk::time_point t0) {
+  const int64_t n = D.n;
   o.solver = FDFD_SOLVER_BICGSTAB; o.precond = FDFD_PRECOND_JACOBI;
-  SellDev D;
-  {
-    SellHost H;
-    std::string err;
-    const int st = csc_to_sell(n, colptr, rowval, nzval, index_base, H, err);
-    if (st != FDFD_OK) { fdfd_set_error(ctx, "fdfd_dolinearsolve_csc: %s", err.c_str()); return st; }
-    FDFD_TRY(sell_upload(ctx, H, D));
-  }
   KrylovWork W;
   FDFD_TRY(W.alloc(ctx, n, D.blocks, o.maxit, true));
   FDFD_TRY(fdfd_copy_in(ctx, W.b.p, b, (size_t)n * sizeof(c128)));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  const double setup_ms = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
-
+  const double setup_ms = ms_since(t0);
   KrylovOps k;
   k.prec_f32 = false; k.prec_rhs = nullptr; k.fscale = 1.0;
   k.nab = D.blocks;
@@ -213,7 +218,7 @@ extern "C" int fdfd_dolinearsolve_csc(fdfd_ctx* ctx, int64_t n, const int64_t* c
   inf.mg_levels = 0;
   FDFD_TRY(fdfd_copy_out(ctx, x, W.x.p, (size_t)n * sizeof(c128)));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  inf.total_ms = std::chrono::duration<double, std::milli>(clk::now() - t0).count();
+  inf.total_ms = ms_since(t0);
   if (info) *info = inf;
   if (inf.flag != FDFD_OK) {
     fdfd_set_error(ctx, "fdfd_dolinearsolve_csc: Krylov solver stopped with flag %d after %d iterations, relres %.3e", inf.flag, inf.iters, inf.relres);
@@ -222,10 +227,128 @@ extern "C" int fdfd_dolinearsolve_csc(fdfd_ctx* ctx, int64_t n, const int64_t* c
   return FDFD_OK;
 }
 
+// (|a - b|^2, |a|^2) summed on the host from the per-CTA partials (fixed order)
+int diff_norms(fdfd_ctx* ctx, int64_t n, const c128* a, const c128* b, DevBuf<double>& parts, int nb, double out[2]) {
+  k_diff_norms<<<nb, kSpThreads, 0, ctx->stream>>>(n, a, b, parts.p); KLAUNCH(ctx);
+  CUDA_TRY(ctx, cudaGetLastError());
+  std::vector<double> h((size_t)nb * 2);
+  CUDA_TRY(ctx, cudaMemcpyAsync(h.data(), parts.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  out[0] = out[1] = 0.0;
+  for (int i = 0; i < nb; ++i) { out[0] += h[2 * i]; out[1] += h[2 * i + 1]; }
+  return FDFD_OK;
+}
+
+int check_csc_args(fdfd_ctx* ctx, int64_t n, const int64_t* colptr, const int64_t* rowval, const fdfd_c128* nzval, int index_base,
+                   const fdfd_c128* b, fdfd_c128* x) {
+  ARG_CHECK(ctx, n >= 1 && n < ((int64_t)1 << 31), "n must be in [1, 2^31)");
+  ARG_CHECK(ctx, colptr && rowval && nzval && b && x, "NULL argument");
+  ARG_CHECK(ctx, index_base == 0 || index_base == 1, "index_base must be 0 or 1");
+  return FDFD_OK;
+}
+
+}  // namespace
+
+// dolinearsolve(A::SparseMatrixCSC{ComplexF64,Int64}, b, matrixsym) -> x   (src/solver/solver.jl:4-41; matrixsym is ignored there too, :29).
+// colptr / rowval / nzval are HOST arrays exactly as Julia stores them (A.colptr, A.rowval, A.nzval; index_base 1) or 0-based;
+// b and x may be host or device pointers.  Solver: BiCGSTAB + Jacobi on the SELL-32 image of A; opts->tol / maxit / check_every /
+// use_graph / verbose are honoured, the preconditioner choice is not (a matrix has no grid to build a multigrid hierarchy from).
+extern "C" int fdfd_dolinearsolve_csc(fdfd_ctx* ctx, int64_t n, const int64_t* colptr, const int64_t* rowval, const fdfd_c128* nzval,
+                                      int index_base, const fdfd_c128* b, const fdfd_solve_opts_t* opts, fdfd_c128* x, fdfd_info_t* info) {
+  ARG_CHECK(ctx, ctx != nullptr, "ctx is NULL");
+  FDFD_TRY(check_csc_args(ctx, n, colptr, rowval, nzval, index_base, b, x));
+  const auto t0 = clk::now();
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  fdfd_solve_opts_t o;
+  if (opts) o = *opts; else fdfd_default_opts(&o);
+  SellDev D;
+  {
+    SellHost H;
+    std::string err;
+    const int st = csc_to_sell(n, colptr, rowval, nzval, index_base, H, err);
+    if (st != FDFD_OK) { fdfd_set_error(ctx, "fdfd_dolinearsolve_csc: %s", err.c_str()); return st; }
+    FDFD_TRY(sell_upload(ctx, H, D));
+  }
+  return solve_generic(ctx, D, b, o, x, info, t0);
+}
+
+// The same seam with the grid the matrix was assembled on (the caller of dolinearsolve always has one: solver.jl's callers build A
+// from d.grid, nonlinear.jl:58-66).  If A turns out to BE the TM operator of that grid at omega for SOME permittivity -- the first
+// solve of nonlinear.jl:66-69 and every Born step A + Diagonal(coeff |ez|^2) (nonlinear.jl:97) are -- the solve runs on the fast
+// path: eps_eff = (A 1) / (w^2 eps0 L0) is read off the row sums (a difference stencil annihilates constants), the matrix-free
+// operator + multigrid hierarchy are built from (grid, omega, eps_eff), and A v == A_matrixfree v is CHECKED on the device with a
+// pseudo-random v (relative 1e-9, both derivative orderings tried) before the multigrid-preconditioned solver is trusted with it.
+// Anything else (the 2N x 2N Gauss-Newton Jacobian of nonlinear.jl:120, a TE matrix, another grid) falls back to the generic path.
+// The residual reported in info->relres is recomputed against the CALLER'S matrix.  info->mg_levels > 0 tells the fast path ran.
+extern "C" int fdfd_dolinearsolve_csc_grid(fdfd_ctx* ctx, const fdfd_grid_t* g, double omega, int64_t n, const int64_t* colptr,
+                                           const int64_t* rowval, const fdfd_c128* nzval, int index_base, const fdfd_c128* b,
+                                           const fdfd_solve_opts_t* opts, fdfd_c128* x, fdfd_info_t* info) {
+  ARG_CHECK(ctx, ctx != nullptr, "ctx is NULL");
+  FDFD_TRY(check_csc_args(ctx, n, colptr, rowval, nzval, index_base, b, x));
+  FDFD_TRY(check_grid(ctx, g));
+  ARG_CHECK(ctx, omega > 0, "omega must be > 0");
+  const auto t0 = clk::now();
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  fdfd_solve_opts_t o;
+  if (opts) o = *opts; else fdfd_default_opts(&o);
+  SellDev D;
+  std::vector<c128> eps_eff;
+  {
+    SellHost H;
+    std::string err;
+    const int st = csc_to_sell(n, colptr, rowval, nzval, index_base, H, err);
+    if (st != FDFD_OK) { fdfd_set_error(ctx, "fdfd_dolinearsolve_csc_grid: %s", err.c_str()); return st; }
+    FDFD_TRY(sell_upload(ctx, H, D));
+    if (n == g->Nx * g->Ny) {
+      const double s = 1.0 / (omega * omega * kEps0 * g->L0);   // TM mass term: w^2 eps0 L0 eps_r (driven.jl:35, device.jl:40)
+      eps_eff.resize(n);
+      for (int64_t i = 0; i < n; ++i) eps_eff[i] = c128(s * H.rowsum[i].x, s * H.rowsum[i].y);
+    }
+  }
+  const bool want_mg = o.solver == FDFD_SOLVER_BICGSTAB && o.precond == FDFD_PRECOND_MG;
+  if (!eps_eff.empty() && want_mg) {
+    for (int ordering : {FDFD_ORDER_FB, FDFD_ORDER_BF}) {
+      fdfd_problem* P = nullptr;
+      FDFD_TRY(fdfd_problem_create(ctx, g, FDFD_TM, ordering, omega, reinterpret_cast<const fdfd_c128*>(eps_eff.data()), &o, &P));
+      struct Guard { fdfd_problem* p; ~Guard() { fdfd_problem_destroy(p); } } guard{P};
+      // is A the matrix-free operator?  p = probe vector, v = A_matrixfree p, s = A p  (p, v, s are re-initialised by the solve)
+      DevBuf<double> parts;
+      const int nb = P->w.nvec_blocks;
+      CUDA_TRY(ctx, parts.alloc((size_t)nb * 2));
+      k_probe_fill<<<nb, 256, 0, ctx->stream>>>(n, P->w.p.p); KLAUNCH(ctx);
+      DotSpec d0;
+      FDFD_TRY(launch_apply(ctx, P->op.view(), false, P->w.p.p, false, P->w.v.p, d0));
+      FDFD_TRY(sell_apply(ctx, D, P->w.p.p, P->w.s.p, d0));
+      double nn[2];
+      FDFD_TRY(diff_norms(ctx, n, P->w.s.p, P->w.v.p, parts, nb, nn));
+      const double opdiff = nn[1] > 0.0 ? std::sqrt(nn[0] / nn[1]) : 1.0;
+      if (o.verbose) fprintf(stderr, "[fdfd_b200] dolinearsolve: |A v - A_matrixfree v| / |A v| = %.3e (ordering %d)\n", opdiff, ordering);
+      if (!(opdiff <= 1e-9)) continue;
+      FDFD_TRY(fdfd_problem_set_rhs(P, b));
+      fdfd_info_t inf{};
+      FDFD_TRY(fdfd_problem_solve(P, &inf));
+      // residual against the caller's matrix: t = A x
+      FDFD_TRY(sell_apply(ctx, D, P->w.x.p, P->w.t.p, d0));
+      FDFD_TRY(diff_norms(ctx, n, P->w.b.p, P->w.t.p, parts, nb, nn));
+      inf.relres = nn[1] > 0.0 ? std::sqrt(nn[0] / nn[1]) : 0.0;
+      if (inf.flag == FDFD_OK && !(inf.relres <= 10.0 * o.tol)) inf.flag = FDFD_ERR_NOCONV;
+      FDFD_TRY(fdfd_problem_get_solution(P, x));
+      inf.total_ms = ms_since(t0);
+      if (info) *info = inf;
+      if (inf.flag != FDFD_OK) {
+        fdfd_set_error(ctx, "fdfd_dolinearsolve_csc_grid: solver stopped with flag %d after %d iterations, relres %.3e", inf.flag, inf.iters, inf.relres);
+        return inf.flag;
+      }
+      return FDFD_OK;
+    }
+  }
+  return solve_generic(ctx, D, b, o, x, info, t0);
+}
+
 // host-only test hook (no GPU needed): y = A x through the SAME CSC -> SELL-32 transposition and the same per-row summation as the
 // kernel; also returns the padded entry count and the inverse diagonal the Jacobi preconditioner would use
 extern "C" int fdfd_debug_sell_spmv(int64_t n, const int64_t* colptr, const int64_t* rowval, const fdfd_c128* nzval, int index_base,
-                                    const fdfd_c128* x, fdfd_c128* y, fdfd_c128* dinv, int64_t* padded_entries) {
+                                    const fdfd_c128* x, fdfd_c128* y, fdfd_c128* dinv, fdfd_c128* rowsum, int64_t* padded_entries) {
   if (n < 1 || n >= ((int64_t)1 << 31) || !colptr || !rowval || !nzval || !x || !y || !(index_base == 0 || index_base == 1)) return FDFD_ERR_ARG;
   SellHost H;
   std::string err;
@@ -240,6 +363,7 @@ extern "C" int fdfd_debug_sell_spmv(int64_t n, const int64_t* colptr, const int6
       if (i < n) yy[i] = out;
     }
   if (dinv) std::memcpy(dinv, H.dinv.data(), sizeof(c128) * n);
+  if (rowsum) std::memcpy(rowsum, H.rowsum.data(), sizeof(c128) * n);
   if (padded_entries) *padded_entries = H.sptr[H.nslices];
   return FDFD_OK;
 }

@@ -178,4 +178,20 @@ function dolinearsolve_b200(A::SparseMatrixCSC, b::AbstractVector; tol::Float64=
     return x
 end
 
+# With the grid and frequency the matrix was assembled on (nonlinear.jl has both in scope at :58-69 and passes them down to
+# _doborn): a matrix that IS the TM operator of that grid -- the first solve and every Born step -- runs on the multigrid path
+# (fdfd_dolinearsolve_csc_grid checks A*v against the matrix-free operator on the device first; anything else falls back).
+function dolinearsolve_b200(A::SparseMatrixCSC, b::AbstractVector, grid::Grid{2}, ω::Real; tol::Float64=1e-10, maxit::Int=20000)
+    n = size(A, 1); n == size(A, 2) == length(b) || error("dolinearsolve_b200: dimension mismatch")
+    colptr = Vector{Int64}(A.colptr); rowval = Vector{Int64}(A.rowval); nzval = Vector{ComplexF64}(A.nzval)
+    bb = Vector{ComplexF64}(b); x = Vector{ComplexF64}(undef, n)
+    opts = COpts(); opts.tol = tol; opts.maxit = maxit; info = CInfo()
+    GC.@preserve colptr rowval nzval bb x check(ccall((:fdfd_dolinearsolve_csc_grid, LIB), Cint,
+        (Ptr{Cvoid}, Ref{CGrid}, Float64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{ComplexF64}, Cint, Ptr{ComplexF64}, Ref{COpts},
+         Ptr{ComplexF64}, Ref{CInfo}),
+        ctx(), CGrid(grid), Float64(ω), n, colptr, rowval, nzval, 1, bb, opts, x, info))
+    @info "fdfd_b200 dolinearsolve ($(info.mg_levels > 0 ? "multigrid" : "generic") path): $(info.iters) iterations, relres $(info.relres)"
+    return x
+end
+
 end # module

@@ -265,10 +265,20 @@ int fdfd_comm_stats(fdfd_comm* comm, int64_t* n_exchange, int64_t* n_allreduce, 
  * driven / modulated / eigenfrequency entry points above are the fast ones.  opts: tol, maxit, check_every, use_graph, verbose. */
 int fdfd_dolinearsolve_csc(fdfd_ctx* ctx, int64_t n, const int64_t* colptr, const int64_t* rowval, const fdfd_c128* nzval,
                            int index_base, const fdfd_c128* b, const fdfd_solve_opts_t* opts, fdfd_c128* x, fdfd_info_t* info);
+/* The same seam with the grid the matrix was assembled on (every caller of dolinearsolve has one, nonlinear.jl:58-66).  If A IS the
+ * TM operator of g at omega for some permittivity -- the first solve (nonlinear.jl:66-69) and every Born step
+ * A + Diagonal(coeff |ez|^2) (nonlinear.jl:97) are -- eps_eff = (A 1)/(w^2 eps0 L0) is read off the row sums, A v == A_matrixfree v
+ * is checked on the device (relative 1e-9, both derivative orderings) and the multigrid-preconditioned solver runs
+ * (info->mg_levels > 0); anything else (the 2N x 2N Gauss-Newton Jacobian, nonlinear.jl:120; a TE matrix) takes the generic path of
+ * fdfd_dolinearsolve_csc (info->mg_levels == 0).  info->relres is recomputed against the caller's matrix. */
+int fdfd_dolinearsolve_csc_grid(fdfd_ctx* ctx, const fdfd_grid_t* g, double omega, int64_t n, const int64_t* colptr,
+                                const int64_t* rowval, const fdfd_c128* nzval, int index_base, const fdfd_c128* b,
+                                const fdfd_solve_opts_t* opts, fdfd_c128* x, fdfd_info_t* info);
 /* host-only test hook (no GPU needed): y = A x through the same CSC -> SELL-32 transposition and per-row summation order as the
- * SpMV kernel; dinv (n, optional) = the Jacobi preconditioner's inverse diagonal; padded_entries (optional) = stored entries. */
+ * SpMV kernel; dinv (n, optional) = the Jacobi preconditioner's inverse diagonal; rowsum (n, optional) = A 1, from which the
+ * grid-hinted path reads the permittivity; padded_entries (optional) = stored entries. */
 int fdfd_debug_sell_spmv(int64_t n, const int64_t* colptr, const int64_t* rowval, const fdfd_c128* nzval, int index_base,
-                         const fdfd_c128* x, fdfd_c128* y, fdfd_c128* dinv, int64_t* padded_entries);
+                         const fdfd_c128* x, fdfd_c128* y, fdfd_c128* dinv, fdfd_c128* rowsum, int64_t* padded_entries);
 
 /* host-only test hook (no GPU needed): the small dense complex Hessenberg eigen-solver behind the Ritz pairs of
  * fdfd_eigenfrequency.  H, evecs: column-major n x n; evals: n. */

@@ -165,6 +165,17 @@ def test_dolinearsolve_sell_transposition_host(fdfd):
     x = rng.standard_normal(A.shape[0]) + 1j * rng.standard_normal(A.shape[0])
     y, _, pad = fdfd._sell_spmv_host(A, x)
     assert np.abs(y - A @ x).max() <= 1e-13 * np.abs(A @ x).max() and pad == 5 * A.shape[0]
+    # grid-hinted path (fdfd_dolinearsolve_csc_grid): the permittivity is read back off the row sums, A 1 = w^2 eps0 L0 eps_r,
+    # also after a Born step A + Diagonal(coeff |ez|^2) (nonlinear.jl:97) has changed the diagonal
+    eps0 = O.normalize_parameters(g)[0]
+    dev.eps_r[3, 4] = 2.5 + 0.1j
+    A = O.system_matrix(dev, dev.omega[0], O.TM)[0].tocsc()
+    rs = np.empty(A.shape[0], complex)
+    fdfd._sell_spmv_host(A, x, rowsum=rs)
+    assert np.abs(rs / (dev.omega[0] ** 2 * eps0) - dev.eps_r.ravel(order="F")).max() <= 1e-12
+    kerr = 1e-3 * rng.random(A.shape[0])
+    fdfd._sell_spmv_host((A + sp.diags(dev.omega[0] ** 2 * eps0 * kerr)).tocsc(), x, rowsum=rs)
+    assert np.abs(rs / (dev.omega[0] ** 2 * eps0) - (dev.eps_r.ravel(order="F") + kerr)).max() <= 1e-12
     with pytest.raises(fdfd.FdfdError):
         fdfd._sell_spmv_host((np.array([0, 1, 2]), np.array([0, 5]), np.array([1.0, 1.0])), np.ones(2))
     with pytest.raises(fdfd.FdfdError):

@@ -89,3 +89,66 @@ def test_bad_arguments_and_nonconvergence_are_reported(fdfd):
     with pytest.raises(fdfd.FdfdError):
         fdfd.dolinearsolve(B, np.ones(200), maxit=5)
     assert np.allclose(fdfd.dolinearsolve(A, np.zeros(8)), 0)   # b = 0 -> x = 0
+
+
+# ---- grid-hinted seam (fdfd_dolinearsolve_csc_grid): a matrix that IS the TM operator of the grid runs on the multigrid path -------
+def _waveguide(fdfd):
+    gargs = (0.02, [15, 10], [0.0, 5.0], [-1.0, 1.0])   # 250 x 100
+    g, go = fdfd.Grid(*gargs), O.Grid2D(*gargs)
+    do = O.Device(go, [W200])
+    xs, ys = O.xc(go)[:, None], O.yc(go)[None, :]
+    do.eps_r[(np.abs(ys) <= 0.15) & (xs >= 0)] = 12.0
+    O.setup_src_point(do, (1.0, 0.0))
+    return g, go, do
+
+
+def test_grid_hint_runs_the_multigrid_path_on_the_reference_matrix(fdfd):
+    g, go, do = _waveguide(fdfd)
+    A, b, _ = O.system_matrix(do, W200, O.TM)
+    A = A.tocsc()
+    x, info = fdfd.dolinearsolve(A, b, grid=g, omega=W200, return_info=True)
+    assert info["flag"] == 0 and info["mg_levels"] > 0 and info["relres"] <= RES_TOL
+    assert np.linalg.norm(b - A @ x) / np.linalg.norm(b) <= 2 * RES_TOL
+    assert rel(x, spla.spsolve(A, b)) <= FIELD_TOL
+    # 1-based Julia arrays, and the reference driver on top of the seam
+    f = O.solve(do, O.TM, linsolve=lambda A_, b_: fdfd.dolinearsolve(A_, b_, grid=g, omega=W200))
+    assert rel(f["data"], O.solve(do, O.TM)["data"]) <= FIELD_TOL
+    x1 = fdfd.dolinearsolve((A.indptr + 1, A.indices + 1, A.data), b, index_base=1, grid=g, omega=W200)
+    assert rel(x1, x) <= 1e-8
+
+
+def test_grid_hint_born_iteration_of_the_kerr_solver(fdfd):
+    """_doborn (nonlinear.jl:92-106): ez <- dolinearsolve(A + Diagonal(coeff |ez|^2), b) until the step is small; every system is a TM
+    operator with a modified permittivity, so every step takes the multigrid path; the iterates equal those of the direct solver"""
+    g, go, do = _waveguide(fdfd)
+    A, b, _ = O.system_matrix(do, W200, O.TM)
+    A = A.tocsc()
+    eps0 = O.normalize_parameters(go)[0]
+    chi = np.where(do.eps_r.ravel(order="F").real > 1, 1.0, 0.0)
+    ez_ref = spla.spsolve(A, b)
+    coeff = W200 ** 2 * eps0 * 3 * chi * (0.05 / np.abs(ez_ref).max() ** 2)   # chi3 scaled to a 5 % index change at the field maximum
+    ez, _ = fdfd.dolinearsolve(A, b, grid=g, omega=W200, return_info=True)
+    for _ in range(3):
+        An = (A + sp.diags(coeff * np.abs(ez_ref) ** 2)).tocsc()
+        ez_ref = spla.spsolve(An, b)
+        Ag = (A + sp.diags(coeff * np.abs(ez) ** 2)).tocsc()
+        ez, info = fdfd.dolinearsolve(Ag, b, grid=g, omega=W200, return_info=True)
+        assert info["flag"] == 0 and info["mg_levels"] > 0 and info["relres"] <= RES_TOL
+        assert rel(ez, ez_ref) <= 1e-5
+
+
+def test_grid_hint_other_ordering_and_fallback(fdfd):
+    g = fdfd.Grid(0.06, [10, 10], [-3, 3], [-3, 3])
+    d = fdfd.Device(g, W200)
+    fdfd.setup_src(d, fdfd.Point(0, 0))
+    b = 1j * W200 * np.asarray(d.src).ravel(order="F")
+    # the b.f ordering of modulation.jl:82 is recognised too
+    trip = fdfd.assemble_system(g, fdfd.TM, W200, d.eps_r, ordering=fdfd._lib.ORDER_BF, fmt=fdfd._lib.CSC, index_base=0)
+    x, info = fdfd.dolinearsolve(trip, b, grid=g, omega=W200, return_info=True)
+    assert info["flag"] == 0 and info["mg_levels"] > 0 and info["relres"] <= RES_TOL
+    # a matrix that is NOT the operator of this grid (here 2 A: the row sums give 2 eps, the couplings do not match) falls back
+    colptr, rowval, nzval = fdfd.assemble_system(g, fdfd.TM, W200, d.eps_r, fmt=fdfd._lib.CSC, index_base=0)
+    x2, info2 = fdfd.dolinearsolve((colptr, rowval, 2 * nzval), b, grid=g, omega=W200, maxit=100000, check_every=64, return_info=True)
+    assert info2["flag"] == 0 and info2["mg_levels"] == 0 and info2["relres"] <= RES_TOL
+    xa = fdfd.dolinearsolve((colptr, rowval, nzval), b, grid=g, omega=W200)
+    assert rel(2 * x2, xa) <= FIELD_TOL
