@@ -3,6 +3,7 @@ compiled for sm_100a so far:
 
   test_mlkrylov.py    multilevel Krylov solver                       (csrc/mlkrylov.cu,   FDFD_SOLVER_MLKRYLOV)
   test_slab_multi.py  slab-sharded modulated / eigenfrequency solves (csrc/slab_multi.cu)
+  test_runtests_exact.py  the reference's three tests (test/runtests.jl) at their exact sizes and isapprox tolerance (verified entry points, new sizes)
   test_dolinearsolve.py  dolinearsolve(A, b) seam on an assembled CSC matrix (csrc/linsolve.cu, fdfd_dolinearsolve_csc)
 
 They carry the marker `gpu_unverified` (NOT `gpu`) and are skipped unless FDFD_RUN_UNVERIFIED=1, so neither the CPU run
