@@ -67,7 +67,7 @@ EXPORTS = [
     "fdfd_comm_create_threads", "fdfd_comm_destroy", "fdfd_slab_rows", "fdfd_solve_driven_slab", "fdfd_comm_stats",
     "fdfd_solve_modulated_slab", "fdfd_eigenfrequency_slab", "fdfd_problem_ml_cycles",
     "fdfd_debug_ml_lsq", "fdfd_debug_ml_transfer", "fdfd_debug_ml_lsq_gpu", "fdfd_debug_ml_transfer_gpu",
-    "fdfd_dolinearsolve_csc", "fdfd_dolinearsolve_csc_grid", "fdfd_debug_sell_spmv",
+    "fdfd_dolinearsolve_csc", "fdfd_dolinearsolve_csc_grid", "fdfd_debug_sell_spmv", "fdfd_debug_sell_bench",
 ]
 COMM_THREADS, COMM_NCCL = 0, 1
 COMM_ID_BYTES = 128
@@ -133,6 +133,7 @@ def lib():
         L.fdfd_eigenfrequency_slab.argtypes = [vp, vp, G, i32, dbl, i32, i32, i32, vp, C.POINTER(SolveOpts), vp, vp, C.POINTER(Info)]
         L.fdfd_dolinearsolve_csc.argtypes = [vp, i64, vp, vp, vp, i32, vp, C.POINTER(SolveOpts), vp, C.POINTER(Info)]
         L.fdfd_dolinearsolve_csc_grid.argtypes = [vp, G, dbl, i64, vp, vp, vp, i32, vp, C.POINTER(SolveOpts), vp, C.POINTER(Info)]
+        L.fdfd_debug_sell_bench.argtypes = [vp, i64, vp, vp, vp, i32, i32, C.POINTER(dbl), C.POINTER(dbl)]
         L.fdfd_debug_sell_spmv.argtypes = [i64, vp, vp, vp, i32, vp, vp, vp, vp, C.POINTER(i64)]
         L.fdfd_comm_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
         _lib = L

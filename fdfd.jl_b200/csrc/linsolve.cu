@@ -345,6 +345,49 @@ extern "C" int fdfd_dolinearsolve_csc_grid(fdfd_ctx* ctx, const fdfd_grid_t* g, 
   return solve_generic(ctx, D, b, o, x, info, t0);
 }
 
+// measurement hook (GPU): average duration in ms of `reps` launches of the SELL-32 SpMV with the two fused dots (the variant the
+// BiCGSTAB loop runs most), CUDA events on the ctx stream after 3 warm-up launches; *alg_bytes = algorithmic bytes per launch
+// (per stored entry 16 + 4 + a 16-byte gathered x; per row 16 for y + 16 for the dot operand)
+extern "C" int fdfd_debug_sell_bench(fdfd_ctx* ctx, int64_t n, const int64_t* colptr, const int64_t* rowval, const fdfd_c128* nzval,
+                                     int index_base, int reps, double* ms_per_launch, double* alg_bytes) {
+  ARG_CHECK(ctx, ctx != nullptr, "ctx is NULL");
+  ARG_CHECK(ctx, n >= 1 && n < ((int64_t)1 << 31) && colptr && rowval && nzval && reps >= 1 && ms_per_launch, "bad arguments");
+  ARG_CHECK(ctx, index_base == 0 || index_base == 1, "index_base must be 0 or 1");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  SellDev D;
+  int64_t stored = 0;
+  {
+    SellHost H;
+    std::string err;
+    const int st = csc_to_sell(n, colptr, rowval, nzval, index_base, H, err);
+    if (st != FDFD_OK) { fdfd_set_error(ctx, "fdfd_debug_sell_bench: %s", err.c_str()); return st; }
+    stored = H.sptr[H.nslices];
+    FDFD_TRY(sell_upload(ctx, H, D));
+  }
+  DevBuf<c128> x, y, d, parts;
+  CUDA_TRY(ctx, x.alloc(n)); CUDA_TRY(ctx, y.alloc(n)); CUDA_TRY(ctx, d.alloc(n)); CUDA_TRY(ctx, parts.alloc((size_t)D.blocks * 2));
+  const int nb = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->num_sms * 8);
+  k_probe_fill<<<nb, 256, 0, ctx->stream>>>(n, x.p); KLAUNCH(ctx);
+  k_probe_fill<<<nb, 256, 0, ctx->stream>>>(n, d.p); KLAUNCH(ctx);
+  DotSpec ds; ds.ndot = 2; ds.d0 = d.p; ds.partials = parts.p;
+  for (int i = 0; i < 3; ++i) FDFD_TRY(sell_apply(ctx, D, x.p, y.p, ds));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(ctx, cudaEventCreate(&e0)); CUDA_TRY(ctx, cudaEventCreate(&e1));
+  CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
+  int st = FDFD_OK;
+  for (int i = 0; i < reps && st == FDFD_OK; ++i) st = sell_apply(ctx, D, x.p, y.p, ds);
+  cudaEventRecord(e1, ctx->stream);
+  cudaEventSynchronize(e1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  FDFD_TRY(st);
+  CUDA_TRY(ctx, cudaGetLastError());
+  *ms_per_launch = (double)ms / reps;
+  if (alg_bytes) *alg_bytes = 36.0 * (double)stored + 32.0 * (double)n;
+  return FDFD_OK;
+}
+
 // host-only test hook (no GPU needed): y = A x through the SAME CSC -> SELL-32 transposition and the same per-row summation as the
 // kernel; also returns the padded entry count and the inverse diagonal the Jacobi preconditioner would use
 extern "C" int fdfd_debug_sell_spmv(int64_t n, const int64_t* colptr, const int64_t* rowval, const fdfd_c128* nzval, int index_base,

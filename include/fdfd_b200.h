@@ -274,6 +274,10 @@ int fdfd_dolinearsolve_csc(fdfd_ctx* ctx, int64_t n, const int64_t* colptr, cons
 int fdfd_dolinearsolve_csc_grid(fdfd_ctx* ctx, const fdfd_grid_t* g, double omega, int64_t n, const int64_t* colptr,
                                 const int64_t* rowval, const fdfd_c128* nzval, int index_base, const fdfd_c128* b,
                                 const fdfd_solve_opts_t* opts, fdfd_c128* x, fdfd_info_t* info);
+/* measurement hook (GPU): average ms of `reps` launches of the SELL-32 SpMV with two fused dots (CUDA events on the ctx stream,
+ * 3 warm-up launches) and the algorithmic bytes of one launch (36 B per stored entry + 32 B per row). */
+int fdfd_debug_sell_bench(fdfd_ctx* ctx, int64_t n, const int64_t* colptr, const int64_t* rowval, const fdfd_c128* nzval,
+                          int index_base, int reps, double* ms_per_launch, double* alg_bytes);
 /* host-only test hook (no GPU needed): y = A x through the same CSC -> SELL-32 transposition and per-row summation order as the
  * SpMV kernel; dinv (n, optional) = the Jacobi preconditioner's inverse diagonal; rowsum (n, optional) = A 1, from which the
  * grid-hinted path reads the permittivity; padded_entries (optional) = stored entries. */

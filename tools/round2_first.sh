@@ -14,6 +14,7 @@ echo "== 4. slab-sharded modulated / eigenfrequency (unverified)" | tee -a gpuru
 FDFD_RUN_UNVERIFIED=1 timeout 1200 python -m pytest tests/unverified/test_slab_multi.py -x -q --timeout 600 2>&1 | tail -15 | tee -a gpurun_out/r2_first.log
 echo "== 4b. dolinearsolve seam on an assembled CSC matrix (unverified)" | tee -a gpurun_out/r2_first.log
 FDFD_RUN_UNVERIFIED=1 timeout 600 python -m pytest tests/unverified/test_dolinearsolve.py -x -q --timeout 300 2>&1 | tail -15 | tee -a gpurun_out/r2_first.log
+timeout 600 python tools/gpu_linsolve.py 512 1024 2048 2>&1 | tail -12 | tee -a gpurun_out/r2_first.log
 echo "== 4c. runtests.jl at exact sizes and isapprox tolerance (unverified sizes)" | tee -a gpurun_out/r2_first.log
 FDFD_RUN_UNVERIFIED=1 timeout 900 python -m pytest tests/unverified/test_runtests_exact.py -x -q -s --timeout 400 2>&1 | tail -15 | tee -a gpurun_out/r2_first.log
 echo "== 5. bench line with the multilevel solver (only meaningful if step 2 was green)" | tee -a gpurun_out/r2_first.log
