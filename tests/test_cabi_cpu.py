@@ -176,6 +176,12 @@ def test_dolinearsolve_sell_transposition_host(fdfd):
     kerr = 1e-3 * rng.random(A.shape[0])
     fdfd._sell_spmv_host((A + sp.diags(dev.omega[0] ** 2 * eps0 * kerr)).tocsc(), x, rowsum=rs)
     assert np.abs(rs / (dev.omega[0] ** 2 * eps0) - (dev.eps_r.ravel(order="F") + kerr)).max() <= 1e-12
+    # ... and the operator rebuilt from (grid, omega, eps_eff) IS the caller's matrix, entry by entry: the premise of the fast path
+    Ab = (A + sp.diags(dev.omega[0] ** 2 * eps0 * kerr)).tocsr()
+    dev2 = O.Device(g, [dev.omega[0]])
+    dev2.eps_r[:] = (rs / (dev.omega[0] ** 2 * eps0)).reshape(dev.eps_r.shape, order="F")
+    A2 = O.system_matrix(dev2, dev.omega[0], O.TM)[0].tocsr()
+    assert abs(Ab - A2).max() <= 1e-12 * abs(Ab).max()
     with pytest.raises(fdfd.FdfdError):
         fdfd._sell_spmv_host((np.array([0, 1, 2]), np.array([0, 5]), np.array([1.0, 1.0])), np.ones(2))
     with pytest.raises(fdfd.FdfdError):
