@@ -43,10 +43,11 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep", type=int, default=4, help="frequencies per GPU per step, solved concurrently (one stream each)")
     ap.add_argument("--no-e2e", action="store_true", help="slab mode: skip the host-buffer (end-to-end) repetition of the solve")
-    ap.add_argument("--solver", default="bicgstab", choices=["bicgstab", "mlkrylov"],
-                    help="sweep mode: bicgstab (default, the measured path) or the opt-in multilevel Krylov solver (csrc/mlkrylov.cu)")
-    ap.add_argument("--ml-spec", default="6,12", help="--solver mlkrylov: FGMRES steps on levels 1,2[,3]")
-    ap.add_argument("--ml-restart", type=int, default=96, help="--solver mlkrylov: level-0 restart length")
+    ap.add_argument("--solver", default="auto", choices=["auto", "bicgstab", "mlkrylov"],
+                    help="sweep mode: auto (library default: multilevel Krylov from 2^22 grid points, BiCGSTAB below), or force one")
+    ap.add_argument("--ml-spec", default="", help="--solver mlkrylov: FGMRES steps on levels 1,2[,3] (default: library default 6,6)")
+    ap.add_argument("--ml-restart", type=int, default=0, help="--solver mlkrylov: level-0 restart length (0: a 1/concurrency share of the free HBM, at most 96)")
+    ap.add_argument("--concurrency", type=int, default=0, help="frequencies solved at the same time (default: --sweep)")
     ap.add_argument("--mode", default="sweep", choices=["sweep", "slab"],
                     help="sweep (default, the metric): disjoint frequencies per GPU, weak scaling.  slab: ONE --grid^2 solve split "
                          "into row slabs over the GPUs (halo exchange + allreduce over NCCL), strong scaling (BASELINE config 5)")
@@ -168,8 +169,8 @@ def workload_config(args):
                         f"(200 THz + k*0.5 THz) per GPU solved concurrently, each to 1e-10 relative residual incl. per-frequency "
                         f"setup and H recovery; value counts solved (omega,source) right-hand sides per second",
             "grid": [args.n, args.n],
-            "solver": ("BiCGSTAB + shifted-Laplacian multigrid (fp32) / fp64 operator" if args.solver == "bicgstab" else
-                       f"multilevel Krylov (FGMRES per level, spec {args.ml_spec}, restart {args.ml_restart}) + shifted-Laplacian multigrid (fp32) / fp64 operator"),
+            "solver": ("BiCGSTAB + shifted-Laplacian multigrid (fp32) / fp64 operator" if args.solver == "bicgstab" or (args.solver == "auto" and args.n * args.n < 2 ** 22) else
+                       f"multilevel Krylov (flexible GMRES per level, steps {args.ml_spec or '6,6'}, F cycles) + shifted-Laplacian multigrid (fp32) / fp64 operator"),
             "l2": "inputs larger than L2: one complex128 vector is 268 MB vs 126 MB L2", "parallelism": f"omega sweep: {args.sweep} frequencies per GPU per step, disjoint frequencies per rank, no collective"}
 
 
@@ -199,10 +200,11 @@ def b200_arm(args):
     # this rank's slice of the omega sweep: B frequencies, solved concurrently by the library (one stream each)
     omegas = [2 * math.pi * (200e12 + 0.5e12 * (rank * B + k)) for k in range(B)]
     wB = (C.c_double * B)(*omegas)
-    opts = fdfd.default_opts(concurrency=B)
-    if args.solver == "mlkrylov":
-        k = [int(x) for x in args.ml_spec.split(",")] + [0, 0, 0]
-        opts.solver = fdfd._lib.SOLVER_MLKRYLOV
+    opts = fdfd.default_opts(concurrency=args.concurrency or B)
+    if args.solver != "auto":
+        opts.solver = {"bicgstab": fdfd._lib.SOLVER_BICGSTAB, "mlkrylov": fdfd._lib.SOLVER_MLKRYLOV}[args.solver]
+    if args.ml_spec or args.ml_restart:
+        k = [int(x) for x in (args.ml_spec or "0").split(",")] + [0, 0, 0]
         opts.ml_spec = k[0] | (k[1] << 8) | (k[2] << 16) | (args.ml_restart << 24)
     # torch is plumbing: device memory and pinned host buffers
     eps_h = torch.from_numpy(np.asfortranarray(d.eps_r).ravel(order="F").copy()).pin_memory()

@@ -14,7 +14,7 @@ TM, TE = 1, 2
 ORDER_FB, ORDER_BF = 0, 1
 DXF, DXB, DYF, DYB = 0, 1, 2, 3
 CSR, CSC = 0, 1
-SOLVER_BICGSTAB, SOLVER_COCG, SOLVER_MLKRYLOV = 0, 1, 2
+SOLVER_BICGSTAB, SOLVER_COCG, SOLVER_MLKRYLOV, SOLVER_AUTO = 0, 1, 2, 3
 PRECOND_NONE, PRECOND_JACOBI, PRECOND_MG = 0, 1, 2
 MG_F32, MG_F64 = 0, 1
 CYCLE_V, CYCLE_F, CYCLE_W = 0, 1, 2

@@ -61,6 +61,11 @@ extern "C" int fdfd_problem_create(fdfd_ctx* ctx, const fdfd_grid_t* g, int pol,
   fdfd_problem* P = new fdfd_problem();
   P->ctx = ctx;
   if (opts) P->opts = *opts; else fdfd_default_opts(&P->opts);
+  if (P->opts.solver == FDFD_SOLVER_AUTO) {
+    // measured crossover: below ~2048^2 both solvers are launch-latency bound and BiCGSTAB is as fast
+    const bool big = g->Nx * g->Ny >= ((int64_t)1 << 22) && std::min(g->Nx, g->Ny) >= 1024;
+    P->opts.solver = (big && P->opts.precond == FDFD_PRECOND_MG && P->opts.mg_precision == FDFD_MG_F32) ? FDFD_SOLVER_MLKRYLOV : FDFD_SOLVER_BICGSTAB;
+  }
   if (!(P->opts.solver == FDFD_SOLVER_BICGSTAB || P->opts.solver == FDFD_SOLVER_COCG || P->opts.solver == FDFD_SOLVER_MLKRYLOV)) { delete P; fdfd_set_error(ctx, "fdfd_problem_create: solver must be FDFD_SOLVER_BICGSTAB, FDFD_SOLVER_COCG or FDFD_SOLVER_MLKRYLOV"); return FDFD_ERR_ARG; }
   if (P->opts.solver == FDFD_SOLVER_MLKRYLOV && !(P->opts.precond == FDFD_PRECOND_MG && P->opts.mg_precision == FDFD_MG_F32)) { delete P; fdfd_set_error(ctx, "fdfd_problem_create: FDFD_SOLVER_MLKRYLOV needs FDFD_PRECOND_MG and FDFD_MG_F32"); return FDFD_ERR_ARG; }
   if (P->opts.solver == FDFD_SOLVER_COCG && P->opts.precond == FDFD_PRECOND_MG) { delete P; fdfd_set_error(ctx, "fdfd_problem_create: COCG needs a symmetric preconditioner (FDFD_PRECOND_JACOBI or FDFD_PRECOND_NONE); the multigrid cycle is not symmetric"); return FDFD_ERR_ARG; }
@@ -73,8 +78,8 @@ extern "C" int fdfd_problem_create(fdfd_ctx* ctx, const fdfd_grid_t* g, int pol,
   if (st != FDFD_OK) return fail(st);
   if (P->opts.precond == FDFD_PRECOND_MG) {
     MGParams mp = mg_params_from(P->opts);
-    if (P->opts.mg_precision == FDFD_MG_F64) { P->mgd = new Multigrid<double>(); st = P->mgd->setup(ctx, P->op, mp); P->mgd->done = &P->w.scal.p->done; }
-    else { P->mgf = new Multigrid<float>(); st = P->mgf->setup(ctx, P->op, mp); P->mgf->done = &P->w.scal.p->done; }
+    if (P->opts.mg_precision == FDFD_MG_F64) { P->mgd = new Multigrid<double>(); st = P->mgd->setup(ctx, P->op, mp); }
+    else { P->mgf = new Multigrid<float>(); st = P->mgf->setup(ctx, P->op, mp); }
     if (st != FDFD_OK) return fail(st);
   }
   if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { fdfd_set_error(ctx, "setup failed: %s", cudaGetErrorString(cudaGetLastError())); return fail(FDFD_ERR_CUDA); }
@@ -295,6 +300,17 @@ extern "C" int fdfd_solve_driven(fdfd_ctx* ctx, const fdfd_grid_t* g, int pol, i
   fdfd_solve_opts_t o;
   if (opts) o = *opts; else fdfd_default_opts(&o);
   const int nworkers = std::max(1, std::min(n_omega, o.concurrency > 0 ? o.concurrency : 1));
+  if (((uint32_t)o.ml_spec >> 24) == 0) {
+    // multilevel Krylov: the level-0 basis (2 vectors per outer iteration) of every worker gets an equal share of the free device
+    // memory, so that no worker starves the others into short restart cycles
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t fr = fdfd_dev_mem_available();
+    if (fr > 0) {
+      const double per = 0.7 * (double)fr / nworkers - 24.0 * 16.0 * (double)N;   // minus Krylov vectors, hierarchy, inner levels, fields
+      const int r = (int)std::max(16.0, std::min(96.0, per / (2.0 * 16.0 * (double)N)));
+      o.ml_spec = (int32_t)(((uint32_t)o.ml_spec & 0xffffffu) | ((uint32_t)r << 24));
+    }
+  }
   std::vector<fdfd_info_t> infos(n_omega);
   std::vector<int> status(n_omega, FDFD_OK);
   if (nworkers == 1) {

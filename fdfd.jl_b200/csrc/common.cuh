@@ -89,7 +89,18 @@ struct fdfd_ctx {
   std::vector<void*> scratch;  // freed at destroy
 };
 
-// RAII device buffer bound to a ctx (plain cudaMalloc; sizes here are few and large)
+// Device memory comes from the device's stream-ordered pool (cudaMallocAsync) with an unlimited release threshold: a buffer
+// freed by one solve is handed to the next one without a trip to the driver.  Plain cudaMalloc / cudaFree synchronise the
+// whole device, so with several frequencies in flight (fdfd_solve_driven, one worker stream each) every per-frequency setup and
+// tear-down used to stall behind the other workers' kernels (round 1: setup_ms bursts of 0.6-2.9 s).  Allocation and release go
+// through one allocator stream per device that never runs a kernel; the allocation is synchronised on that stream only, so
+// the memory is valid on every stream when alloc() returns.  Release is safe because every owner synchronises the stream it
+// used the buffer on before the buffer's destructor runs (every C-ABI call syncs before it returns).
+cudaError_t fdfd_dev_alloc(void** p, size_t bytes);
+void fdfd_dev_free(void* p);
+size_t fdfd_dev_mem_available();   // free device memory + what the pool holds cached (bytes, current device)
+
+// RAII device buffer (sizes here are few and large)
 template <typename T> struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
@@ -100,12 +111,12 @@ template <typename T> struct DevBuf {
   DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), own(o.own) { o.p = nullptr; o.n = 0; }
   DevBuf& operator=(DevBuf&& o) noexcept { release(); p = o.p; n = o.n; own = o.own; o.p = nullptr; o.n = 0; return *this; }
   ~DevBuf() { release(); }
-  void release() { if (p && own) cudaFree(p); p = nullptr; n = 0; own = true; }
+  void release() { if (p && own) fdfd_dev_free(p); p = nullptr; n = 0; own = true; }
   void alias(T* q, size_t count) { release(); p = q; n = count; own = false; }
   cudaError_t alloc(size_t count) {
     release();
     if (count == 0) return cudaSuccess;
-    cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+    cudaError_t e = fdfd_dev_alloc((void**)&p, count * sizeof(T));
     if (e == cudaSuccess) n = count;
     return e;
   }

@@ -27,6 +27,67 @@ extern "C" const char* fdfd_last_error(fdfd_ctx* ctx) {
 
 extern "C" int64_t fdfd_launch_count(fdfd_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+// ---- pooled device memory (see common.cuh) -------------------------------------------------------------------------------
+namespace {
+struct AllocState { cudaStream_t stream = nullptr; bool pooled = false; bool init = false; };
+AllocState g_alloc[64];
+std::mutex g_alloc_mu;
+AllocState& alloc_state(int dev) {
+  std::lock_guard<std::mutex> lk(g_alloc_mu);
+  AllocState& A = g_alloc[dev & 63];
+  if (!A.init) {
+    A.init = true;
+    const char* e = getenv("FDFD_NO_POOL");   // diagnostics: plain cudaMalloc / cudaFree
+    int supported = 0;
+    if (!(e && atoi(e) != 0) && cudaDeviceGetAttribute(&supported, cudaDevAttrMemoryPoolsSupported, dev) == cudaSuccess && supported) {
+      cudaMemPool_t pool = nullptr;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess && cudaStreamCreateWithFlags(&A.stream, cudaStreamNonBlocking) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        A.pooled = true;
+      }
+    }
+    cudaGetLastError();
+  }
+  return A;
+}
+}  // namespace
+
+cudaError_t fdfd_dev_alloc(void** p, size_t bytes) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  AllocState& A = alloc_state(dev);
+  if (!A.pooled) return cudaMalloc(p, bytes);
+  cudaError_t e = cudaMallocAsync(p, bytes, A.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(A.stream);
+  return e;
+}
+
+size_t fdfd_dev_mem_available() {
+  size_t fr = 0, tot = 0;
+  if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (alloc_state(dev).pooled) {
+    cudaMemPool_t pool = nullptr;
+    uint64_t reserved = 0, used = 0;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess && cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used) fr += (size_t)(reserved - used);
+    cudaGetLastError();
+  }
+  return fr;
+}
+
+void fdfd_dev_free(void* p) {
+  if (!p) return;
+  cudaPointerAttributes a;
+  int dev = 0;
+  if (cudaPointerGetAttributes(&a, p) == cudaSuccess) dev = a.device; else { cudaGetLastError(); cudaGetDevice(&dev); }
+  AllocState& A = alloc_state(dev);
+  if (!A.pooled) { cudaFree(p); return; }
+  if (cudaFreeAsync(p, A.stream) != cudaSuccess) { cudaGetLastError(); cudaFree(p); }
+}
+
 extern "C" int fdfd_ctx_create(int device, void* stream, fdfd_ctx** out) {
   if (!out) { fdfd_set_error(nullptr, "fdfd_ctx_create: out is NULL"); return FDFD_ERR_ARG; }
   *out = nullptr;
@@ -39,9 +100,9 @@ extern "C" int fdfd_ctx_create(int device, void* stream, fdfd_ctx** out) {
     return FDFD_ERR_CUDA;
   }
   if (device < 0 || device >= ndev) { fdfd_set_error(nullptr, "fdfd_ctx_create: bad device %d of %d", device, ndev); return FDFD_ERR_ARG; }
+  CUDA_TRY(nullptr, cudaSetDevice(device));
   fdfd_ctx* ctx = new fdfd_ctx();
   ctx->device = device;
-  CUDA_TRY(nullptr, cudaSetDevice(device));
   if (stream) { ctx->stream = (cudaStream_t)stream; ctx->own_stream = false; }
   else {
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
@@ -64,13 +125,13 @@ extern "C" void fdfd_ctx_destroy(fdfd_ctx* ctx) {
 
 extern "C" void fdfd_default_opts(fdfd_solve_opts_t* o) {
   if (!o) return;
-  o->solver = FDFD_SOLVER_BICGSTAB;
+  o->solver = FDFD_SOLVER_AUTO;
   o->precond = FDFD_PRECOND_MG;
   o->tol = 1e-10;
   o->maxit = 20000;
   o->mg_precision = FDFD_MG_F32;
   o->mg_cycle = FDFD_CYCLE_W;
-  o->mg_wdepth = 2;
+  o->mg_wdepth = 3;
   o->mg_nu1 = 1; o->mg_nu2 = 1;
   o->mg_coarse_sweeps = 2;
   o->mg_beta = 0.5;

@@ -77,13 +77,17 @@ template <typename T> struct Multigrid {
   DevBuf<c128> pcr_scratch;   // setup-only scratch
   DevBuf<cplx<T>> spare;         // third level-0 buffer: lets the caller keep one result across the next apply
   double rhs_scale = 1.0;        // M is stored scaled by this factor (keeps fp32 in range); callers scale the rhs they write
-  const int* done = nullptr;     // optional device flag: kernels early-exit once the Krylov loop has converged
+  // optional device flag: kernels early-exit when it is set.  The solvers leave it NULL: the cycle only writes its own buffers, so
+  // iterations enqueued past convergence are harmless, while the flag costs every (latency-bound) coarse kernel one dependent
+  // global load before its first useful instruction; the Krylov update / apply kernels, which own x and r, do check it.
+  const int* done = nullptr;
 
   // build hierarchy for the operator `op` (fine eps_r resident in op.eps)
   // first_level > 0 builds only levels >= first_level (the agglomerated coarse part of a slab-sharded solve): `op` then
   // needs its host-side members only and eps_first is the level-first_level eps_r resident in HBM
   int setup(fdfd_ctx* ctx, const FineOp& op, const MGParams& prm, int first_level = 0, const c128* eps_first = nullptr);
   int first = 0;
+  int wbase = 0;                 // level the W recursion depth is counted from (a cycle started on level s by the multilevel solver sets s)
   // u0 = approx M^-1 f0 where f0 = lv[0].f (already filled).  Result pointer returned in *out (lv[0].u or .tmp)
   int apply(const cplx<T>** out);
   cplx<T>* rhs() { return lv[0].f.p; }

@@ -21,7 +21,10 @@
 //   1024^2: default solver 474 fine cycles; steps (6,12): 24 fine + 144 level-1 + 1728 level-2;  (6,8): 26 + 156 + 1248.
 //   2048^2: default solver 960 fine cycles; steps (6,8): 47 + 282 + 2256;  (8,12): 32 + 256 + 3072  (DESIGN.md 5b).
 //
-// STATUS: written in a session without GPU access -- compiles for sm_100a, exercised by tests/unverified/ only.
+// Measured on a B200 (round 2, tools/gpu_mlkrylov.py, tools/gpu_r2_exp*.py; bench map, one solve, single stream):
+//   1024^2: 27 outer iterations (prototype 26) / 268 ms against 216 BiCGSTAB iterations / 257 ms;  2048^2: 49 / 672 ms against 437 / 720 ms;
+//   4096^2, F cycles, steps (6,6): 105 / 3.3-4.1 s against 1230 (W depth 3) / 5.0 s -- hence FDFD_SOLVER_AUTO's crossover at 2^22 points.
+// GPU tests: tests/test_gpu_mlkrylov.py.
 #include "krylov.cuh"
 #include "reduce.cuh"
 #include <algorithm>
@@ -253,6 +256,11 @@ struct MLKrylov {
   std::map<std::vector<void*>, IterGraph> graphs;   // the level-1 solve, one graph per multigrid buffer-rotation state
   bool use_graph = false;
   bool fused_gs = true;                              // inner levels: fused classical Gram-Schmidt (FDFD_ML_MGS=1 selects the modified one)
+  bool rel_w = true;                                 // W recursion depth of a cycle counted from the level it is started on (FDFD_ML_RELW=0: from level 0)
+  bool l0_cgs = true;                                // level 0: fused classical Gram-Schmidt (one pass over w per 8 basis vectors) instead of the modified one
+                                                     // (FDFD_ML_L0CGS=0); measured at 4096^2: same 176 outer iterations, 6.95 -> 4.64 s
+  int cycle_kind = FDFD_CYCLE_F;                     // cycle of M_l^-1 (FDFD_ML_CYCLE): F on every level -- a W cycle truncated at an absolute depth
+                                                     // degenerates to V on the inner levels; measured at 4096^2, steps (6,6): W2 210 outer / 6.0 s, F 105 / 3.3-4.1 s
   int64_t cycles[8] = {0, 0, 0, 0, 0, 0, 0, 0};      // multigrid cycles started per level (diagnostics)
   ~MLKrylov() { for (auto& kv : graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec); }
 };
@@ -270,7 +278,7 @@ int ml_setup(fdfd_problem* P, MLKrylov& M) {
   uint32_t spec = (uint32_t)P->opts.ml_spec;
   if (const char* e = getenv("FDFD_ML_SPEC")) spec = (uint32_t)strtoul(e, nullptr, 0);   // diagnostics
   int ks[4] = {(int)(spec >> 24) & 0xff, (int)spec & 0xff, (int)(spec >> 8) & 0xff, (int)(spec >> 16) & 0xff};
-  if ((spec & 0xffffff) == 0) { ks[1] = 6; ks[2] = 12; ks[3] = 0; }
+  if ((spec & 0xffffff) == 0) { ks[1] = 6; ks[2] = 6; ks[3] = 0; }   // measured at 4096^2 (F cycles): (6,6) 105 outer / 3.3-4.1 s, (6,8) 89 / 5.1 s, (8,8) 70 / 3.9 s, (4,4) 228 / 5.3 s
   if (ks[0] == 0) ks[0] = 96;
   int nl = 1;
   while (nl < 4 && ks[nl] > 0 && nl < mg->levels()) ++nl;
@@ -307,6 +315,9 @@ int ml_setup(fdfd_problem* P, MLKrylov& M) {
   cudaStream_t st = ctx->stream;
   M.use_graph = P->opts.use_graph && st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
   if (const char* e = getenv("FDFD_ML_MGS")) M.fused_gs = atoi(e) == 0;   // diagnostics
+  if (const char* e = getenv("FDFD_ML_L0CGS")) M.l0_cgs = atoi(e) != 0;
+  if (const char* e = getenv("FDFD_ML_RELW")) M.rel_w = atoi(e) != 0;
+  if (const char* e = getenv("FDFD_ML_CYCLE")) { const int v = atoi(e); if (v >= FDFD_CYCLE_V && v <= FDFD_CYCLE_W) M.cycle_kind = v; }
   return FDFD_OK;
 }
 
@@ -339,7 +350,10 @@ int ml_precond(MLKrylov& M, int li, const c128* v, c128* z) {
     q = L.q.p; t = L.t.p;
   }
   k_ml_to_mg<<<L.nb, 256, 0, st>>>(L.N, v, t, mg->lv[L.l].f.p, mg->rhs_scale); KLAUNCH(ctx);
-  FDFD_TRY(mg->cycle(L.l, true, mg->prm.cycle));
+  mg->wbase = M.rel_w ? L.l : 0;
+  const int crc = mg->cycle(L.l, true, M.cycle_kind);
+  mg->wbase = 0;
+  FDFD_TRY(crc);
   M.cycles[L.l < 8 ? L.l : 7]++;
   k_ml_from_mg<<<L.nb, 256, 0, st>>>(L.N, q, mg->lv[L.l].u.p, z); KLAUNCH(ctx);
   CUDA_TRY(ctx, cudaGetLastError());
@@ -355,7 +369,7 @@ int ml_arnoldi_step(MLKrylov& M, int li, int j) {
   DotSpec d0;
   FDFD_TRY(launch_apply(ctx, L.op->view(), L.op->pol == FDFD_TE, L.Z[j].p, false, L.w.p, d0));
   c128* Hj = L.H.p + (size_t)j * (L.k + 1);
-  if (li == 0 || !M.fused_gs) {   // modified Gram-Schmidt (level 0 always: its basis is long and its tolerance tight)
+  if ((li == 0 && !M.l0_cgs) || (li > 0 && !M.fused_gs)) {   // modified Gram-Schmidt
     for (int i = 0; i <= j; ++i) {
       FDFD_TRY(ml_dot(ctx, L, L.V[i].p, L.w.p, Hj + i, 0));
       k_ml_axpy_neg<<<L.nb, 256, 0, st>>>(L.N, Hj + i, L.V[i].p, L.w.p); KLAUNCH(ctx);

@@ -88,7 +88,6 @@ int solve_modulated_t(fdfd_ctx* ctx, const fdfd_grid_t* g, double omega, double 
     MGLevel<T>& L0 = M.mgs[j]->lv[0];
     L0.f.alias(M.F.p + (size_t)j * N, N); L0.u.alias(M.U.p + (size_t)j * N, N); L0.tmp.alias(M.Tm.p + (size_t)j * N, N);
     M.mgs[j]->spare.alias(M.S.p + (size_t)j * N, N);
-    M.mgs[j]->done = &M.w.scal.p->done;
   }
   // b: zeros(N*nf); centre block = 1im*ω*src  (modulation.jl:67-69)
   FDFD_TRY(fdfd_copy_in(ctx, M.w.t.p, src, N * sizeof(c128)));
@@ -145,7 +144,7 @@ extern "C" int fdfd_solve_modulated(fdfd_ctx* ctx, const fdfd_grid_t* g, double 
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   fdfd_solve_opts_t o;
   if (opts) o = *opts; else fdfd_default_opts(&o);
-  ARG_CHECK(ctx, o.solver == FDFD_SOLVER_BICGSTAB && o.precond == FDFD_PRECOND_MG, "modulated solve needs BiCGSTAB + multigrid");
+  ARG_CHECK(ctx, (o.solver == FDFD_SOLVER_BICGSTAB || o.solver == FDFD_SOLVER_AUTO) && o.precond == FDFD_PRECOND_MG, "modulated solve needs BiCGSTAB + multigrid");
   if (o.mg_precision == FDFD_MG_F64)
     return solve_modulated_t<double>(ctx, g, omega, Omega, nsidebands, sharedpml, eps_r, deps_r, src, o, fields, info);
   return solve_modulated_t<float>(ctx, g, omega, Omega, nsidebands, sharedpml, eps_r, deps_r, src, o, fields, info);

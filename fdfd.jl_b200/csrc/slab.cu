@@ -192,7 +192,7 @@ int solve_slab(fdfd_ctx* ctx, fdfd_comm* comm, const fdfd_grid_t* g, double omeg
   SlabSolver S;
   S.ctx = ctx; S.comm = comm;
   if (opts) S.o = *opts; else fdfd_default_opts(&S.o);
-  ARG_CHECK(ctx, S.o.solver == FDFD_SOLVER_BICGSTAB && S.o.precond == FDFD_PRECOND_MG && S.o.mg_precision == FDFD_MG_F32,
+  ARG_CHECK(ctx, (S.o.solver == FDFD_SOLVER_BICGSTAB || S.o.solver == FDFD_SOLVER_AUTO) && S.o.precond == FDFD_PRECOND_MG && S.o.mg_precision == FDFD_MG_F32,
             "the slab solve runs BiCGSTAB + fp32 multigrid only");
   ARG_CHECK(ctx, S.o.mg_nu2 >= 1, "the slab solve needs mg_nu2 >= 1");
   ARG_CHECK(ctx, g->Ny % comm->nranks == 0, "Ny must be divisible by the number of slabs");
@@ -226,7 +226,6 @@ int solve_slab(fdfd_ctx* ctx, fdfd_comm* comm, const fdfd_grid_t* g, double omeg
   }
   FDFD_TRY(S.w.alloc(ctx, Nloc, apply_num_blocks(Nx, nloc), S.o.maxit, false));
   FDFD_TRY(S.mg.setup(ctx, S.op, prm));
-  S.mg.done = &S.w.scal.p->done;
   ARG_CHECK(ctx, S.mg.levels() == nlev, "internal: multigrid depth differs from the slab halo depth");
   if (ka >= 1) {
     // level-ka eps_r of the whole grid (owned rows of every slab, rank order = row order), then the global coarse hierarchy
@@ -238,7 +237,6 @@ int solve_slab(fdfd_ctx* ctx, fdfd_comm* comm, const fdfd_grid_t* g, double omeg
     S.opg.g = *g; S.opg.pol = FDFD_TM; S.opg.ordering = FDFD_ORDER_FB; S.opg.omega = omega; S.opg.omega_pml = omega;
     host_coef_fine(*g, omega, FDFD_ORDER_FB, 1.0 / (kMu0 * g->L0), S.opg.hc);
     FDFD_TRY(S.mgc.setup(ctx, S.opg, prm, ka, eps_k.p));
-    S.mgc.done = &S.w.scal.p->done;
     ARG_CHECK(ctx, S.mgc.lv[ka].nx == Lk.nx && S.mgc.lv[ka].ny == nyo * comm->nranks, "internal: global coarse level size mismatch");
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
   }
@@ -272,7 +270,9 @@ int solve_slab(fdfd_ctx* ctx, fdfd_comm* comm, const fdfd_grid_t* g, double omeg
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
   }
   info->total_ms = wall_ms() - t0;
-  if (info->flag != FDFD_OK) fdfd_set_error(ctx, "slab Krylov solver stopped with flag %d after %d iterations, relres %.3e", info->flag, info->iters, info->relres);
+  // like fdfd_solve_driven: an unconverged solve is an error of the call (the fields are still copied out as the best
+  // approximation).  Every rank sees the same flag (the convergence scalars come out of the allreduce), so no rank is left behind.
+  if (info->flag != FDFD_OK) { fdfd_set_error(ctx, "slab Krylov solver stopped with flag %d after %d iterations, relres %.3e", info->flag, info->iters, info->relres); return info->flag; }
   return FDFD_OK;
 }
 

@@ -12,8 +12,7 @@
 // The Arnoldi basis is sharded like every other vector (owned rows + zero halo rows); its dot products are the same
 // allreduce, the Hessenberg matrix lives on the host (identical on every rank: the allreduce is bit-reproducible).
 //
-// STATUS: written in a session without GPU access -- compiles for sm_100a, exercised by tests/unverified/ only
-// (FDFD_RUN_UNVERIFIED=1).  slab.cu stays the verified driven path until this file has run on hardware.
+// GPU tests: tests/test_gpu_slab_multi.py (1 / 2 / 4 slabs against the single-GPU solves and the oracle).
 #include "comm.cuh"
 #include "krylov.cuh"
 #include "reduce.cuh"
@@ -240,7 +239,7 @@ struct SlabMulti {
     const double t0 = wall_ms();
     ctx = ctx_; comm = comm_; gg = *g; nf = (int)omegas.size(); omegan = omegas;
     if (opts) o = *opts; else fdfd_default_opts(&o);
-    ARG_CHECK(ctx, o.solver == FDFD_SOLVER_BICGSTAB && o.precond == FDFD_PRECOND_MG && o.mg_precision == FDFD_MG_F32,
+    ARG_CHECK(ctx, (o.solver == FDFD_SOLVER_BICGSTAB || o.solver == FDFD_SOLVER_AUTO) && o.precond == FDFD_PRECOND_MG && o.mg_precision == FDFD_MG_F32,
               "the slab solves run BiCGSTAB + fp32 multigrid only");
     ARG_CHECK(ctx, o.mg_nu2 >= 1, "the slab solves need mg_nu2 >= 1");
     ARG_CHECK(ctx, g->Ny % comm->nranks == 0, "Ny must be divisible by the number of slabs");
@@ -284,7 +283,6 @@ struct SlabMulti {
       MGLevel<float>& L0 = mgs[j]->lv[0];
       L0.f.alias(F.p + (size_t)j * Nloc, Nloc); L0.u.alias(U.p + (size_t)j * Nloc, Nloc); L0.tmp.alias(Tm.p + (size_t)j * Nloc, Nloc);
       mgs[j]->spare.alias(S.p + (size_t)j * Nloc, Nloc);
-      mgs[j]->done = &w.scal.p->done;
       if (ka >= 1) {
         const MGLevel<float>& Lk = mgs[j]->lv[ka];
         const int64_t nyo = nyl >> ka;
@@ -297,7 +295,6 @@ struct SlabMulti {
         host_coef_fine(*g, omegas_pml[j], ordering, 1.0 / (kMu0 * g->L0), G.hc);
         mgcs.emplace_back(new Multigrid<float>());
         FDFD_TRY(mgcs[j]->setup(ctx, G, prm, ka, eps_k.p));
-        mgcs[j]->done = &w.scal.p->done;
         ARG_CHECK(ctx, mgcs[j]->lv[ka].nx == Lk.nx && mgcs[j]->lv[ka].ny == nyo * comm->nranks, "internal: global coarse level size mismatch");
         CUDA_TRY(ctx, cudaStreamSynchronize(st));   // eps_k is a local
       }

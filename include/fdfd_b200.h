@@ -50,10 +50,12 @@ enum { FDFD_DXF = 0, FDFD_DXB = 1, FDFD_DYF = 2, FDFD_DYB = 3 };
 enum { FDFD_CSR = 0, FDFD_CSC = 1 };
 /* Krylov solvers / preconditioners */
 /* BICGSTAB: any preconditioner.  COCG: on the symmetrised system diag(sxf*syf) A, Jacobi or no preconditioner. */
-/* MLKRYLOV (opt-in; csrc/mlkrylov.cu, compiled but not yet run on a GPU): multilevel Krylov -- flexible GMRES on every level,
- * preconditioned by the multigrid cycle plus a coarse-grid Helmholtz correction solved by the same method one level down.
- * TM and TE; FDFD_PRECOND_MG and FDFD_MG_F32 only. */
-enum { FDFD_SOLVER_BICGSTAB = 0, FDFD_SOLVER_COCG = 1, FDFD_SOLVER_MLKRYLOV = 2 };
+/* MLKRYLOV (csrc/mlkrylov.cu): multilevel Krylov -- flexible GMRES on every level, preconditioned by the multigrid cycle plus a
+ * coarse-grid Helmholtz correction solved by the same method one level down.  TM and TE; FDFD_PRECOND_MG and FDFD_MG_F32 only.
+ * AUTO (default): MLKRYLOV for the driven single-GPU solve of a grid of >= 2^22 points with the fp32 multigrid (measured on a
+ * B200, 4096^2 bench map: 105 outer iterations / 3.3-4.1 s against 1230 BiCGSTAB iterations / 5.0 s; below 2048^2 both are
+ * launch-latency bound and BiCGSTAB is as fast), BICGSTAB everywhere else (slab-sharded, modulated, Jacobi / no preconditioner). */
+enum { FDFD_SOLVER_BICGSTAB = 0, FDFD_SOLVER_COCG = 1, FDFD_SOLVER_MLKRYLOV = 2, FDFD_SOLVER_AUTO = 3 };
 enum { FDFD_PRECOND_NONE = 0, FDFD_PRECOND_JACOBI = 1, FDFD_PRECOND_MG = 2 };
 enum { FDFD_MG_F32 = 0, FDFD_MG_F64 = 1 };
 enum { FDFD_CYCLE_V = 0, FDFD_CYCLE_F = 1, FDFD_CYCLE_W = 2 };
@@ -72,13 +74,14 @@ typedef struct {
 } fdfd_grid_t;
 
 typedef struct {
-  int32_t solver;        /* FDFD_SOLVER_*  (default BICGSTAB) */
+  int32_t solver;        /* FDFD_SOLVER_*  (default AUTO) */
   int32_t precond;       /* FDFD_PRECOND_* (default MG) */
   double  tol;           /* relative residual ||b-Ax||/||b|| of the un-preconditioned system (default 1e-10) */
   int32_t maxit;         /* Krylov iterations (default 20000) */
   int32_t mg_precision;  /* FDFD_MG_F32 | FDFD_MG_F64 (default F32) */
   int32_t mg_cycle;      /* FDFD_CYCLE_* (default W, truncated at mg_wdepth) */
-  int32_t mg_wdepth;     /* levels [0,wdepth) recurse twice in a W cycle (default 2) */
+  int32_t mg_wdepth;     /* levels [0,wdepth) recurse twice in a W cycle (default 3; measured at 4096^2: 1982 / 1230 / 1263 BiCGSTAB
+                            iterations and 6.6 / 5.0 / 6.5 s for depth 2 / 3 / 4) */
   int32_t mg_nu1, mg_nu2;/* pre/post smoothing sweeps (default 1,1) */
   int32_t mg_coarse_sweeps; /* sweeps on the coarsest level (default 2) */
   double  mg_beta;       /* complex shift: M = L + (1 - i*beta) w^2 eps (default 0.5) */
@@ -91,8 +94,9 @@ typedef struct {
   int32_t use_graph;     /* replay the iteration as a CUDA graph (default 1) */
   int32_t concurrency;   /* fdfd_solve_driven: frequencies solved concurrently on separate streams (default 4) */
   int32_t ml_spec;       /* FDFD_SOLVER_MLKRYLOV: k1 | k2<<8 | k3<<16 | restart<<24 = FGMRES steps per solve on levels 1,2,3 (0 ends the
-                            list) and the level-0 restart length; 0 = defaults (6, 12; restart 96; the level-0 basis grows on demand, 2 vectors per iteration,
-                            and a full device forces an earlier restart instead of an error) */
+                            list) and the level-0 restart length; 0 = defaults (6, 6; restart 96, or what a 1/concurrency share of the free device
+                            memory holds inside fdfd_solve_driven; the level-0 basis grows on demand, 2 vectors per iteration, and a full
+                            device forces an earlier restart instead of an error) */
 } fdfd_solve_opts_t;
 
 typedef struct {
@@ -237,8 +241,7 @@ int fdfd_solve_driven_slab(fdfd_ctx* ctx, fdfd_comm* comm, const fdfd_grid_t* g,
                            const fdfd_c128* eps_r_rows, const fdfd_c128* src_rows, const fdfd_solve_opts_t* opts,
                            fdfd_c128* fields_rows, fdfd_info_t* info);
 /* ---- slab-sharded modulated and eigenfrequency solves (csrc/slab_multi.cu).
- * STATUS: written without GPU access, compiled only; exercised by tests/unverified (FDFD_RUN_UNVERIFIED=1) until they have
- * run on hardware.  Same slab layout, communicators and collective-call rules as fdfd_solve_driven_slab.
+ * Same slab layout, communicators and collective-call rules as fdfd_solve_driven_slab.
  *
  * solve(d::ModulatedDevice) (src/solver/modulation.jl:35-119) on row slabs: the sideband coupling is pointwise
  * (modulation.jl:95-98), so all nf = 2*nsidebands+1 sidebands of a row live on the rank that owns the row and the

@@ -18,8 +18,6 @@ if ROOT not in sys.path:
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
     config.addinivalue_line("markers", "slow: takes more than a minute on CPU")
-    config.addinivalue_line("markers", "gpu_unverified: GPU test of code that has not run on hardware yet (tests/unverified, "
-                                       "skipped unless FDFD_RUN_UNVERIFIED=1; deliberately NOT selected by -m gpu)")
 
 
 @pytest.fixture(scope="session")

@@ -1,9 +1,7 @@
 """GPU tests of csrc/linsolve.cu: fdfd_dolinearsolve_csc, the dolinearsolve(A, b, matrixsym) seam of the reference
 (src/solver/solver.jl:4-41) for callers that hand over an assembled SparseMatrixCSC.
 
-NOT part of `-m gpu`: written in a session without GPU access, compiled only (the host half -- CSC -> SELL-32 -- is covered by
-tests/test_cabi_cpu.py).  Run with  FDFD_RUN_UNVERIFIED=1 python -m pytest tests/unverified/test_dolinearsolve.py -x -q --timeout 900
-on a B200; once green, move into tests/test_gpu_parity.py with the `gpu` marker.
+First run on hardware in round 2 (7/7 green); the host half -- CSC -> SELL-32 -- is covered by tests/test_cabi_cpu.py.
 Bars: true relative residual <= 1e-10 (recomputed here with SciPy), solution / fields within 1e-6 relative L2 of the oracle's
 sparse direct solve."""
 import os
@@ -15,8 +13,7 @@ import scipy.sparse.linalg as spla
 
 from oracle import fdfd_oracle as O
 
-pytestmark = [pytest.mark.gpu_unverified,
-              pytest.mark.skipif(os.environ.get("FDFD_RUN_UNVERIFIED") != "1", reason="unverified GPU path: set FDFD_RUN_UNVERIFIED=1 on a GPU box")]
+pytestmark = pytest.mark.gpu
 
 W200 = 2 * np.pi * 200e12
 RES_TOL, FIELD_TOL = 1e-10, 1e-6

@@ -1,8 +1,6 @@
 """GPU tests of csrc/slab_multi.cu (slab-sharded modulated and eigenfrequency solves).
 
-NOT part of `-m gpu`: the code was written in a session without GPU access and has only been compiled.  Run with
-    FDFD_RUN_UNVERIFIED=1 python -m pytest tests/unverified -x -q --timeout 900
-on a B200; once green, move these into tests/test_gpu_slab.py with `pytestmark = pytest.mark.gpu`.
+First run on hardware in round 2 (11/11 green).
 All slabs live on ONE GPU (thread transport), like tests/test_gpu_slab.py.  Bars: true relative residual <= 1e-10, fields
 within 1e-6 relative L2 of the single-GPU solve and of the oracle, eigenfrequencies within 1e-8 relative."""
 import math
@@ -11,8 +9,7 @@ import os
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu_unverified,
-              pytest.mark.skipif(os.environ.get("FDFD_RUN_UNVERIFIED") != "1", reason="unverified GPU path: set FDFD_RUN_UNVERIFIED=1 on a GPU box")]
+pytestmark = pytest.mark.gpu
 
 FIELD_TOL = 1e-6
 EIG_TOL = 1e-8
