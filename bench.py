@@ -10,7 +10,11 @@ setup (PML coefficients, multigrid hierarchy), the GPU-resident Krylov solve to 
 the fp64 operator) and H-field recovery; the library overlaps the frequencies on separate streams.  The metric counts
 solved (omega, source) right-hand sides per second.  `value` times that with eps_r/src resident in HBM; `e2e` times the
 public API call (`solve(device)`) with host buffers, H2D and D2H copies inside the timed region.  N > 1: one rank
-per GPU, each rank solves its own frequency of an omega sweep (no data-path collective): weak scaling.
+per GPU, every rank solves a sweep of the same --sweep frequencies on its own copy of the device (independent units, no
+data-path collective): weak scaling with identical work per GPU.  (Round 1 gave rank r the frequencies 200 + 0.5 (4 r + k) THz:
+the iteration count grows with frequency, so the MAX over ranks measured the hardest frequency set, not the machine.)
+With --slab-grid G (default 8192 when N > 1) the same launch also times ONE G x G solve split into row slabs over the N ranks
+(halo exchange + allreduce over NCCL, strong scaling) and reports it under "slab" in the same JSON line.
 """
 import argparse
 import json
@@ -39,7 +43,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--grid", dest="n", type=int, default=4096, help="grid edge (cells); 4096 is the metric's configuration")
     ap.add_argument("--density", type=float, default=1.0 / 160.0, help="scatterers per um^2 of the synthetic map")
-    ap.add_argument("--ref-grid", dest="ref_n", type=int, default=512, help="grid edge of the bounded CPU sample")
+    ap.add_argument("--ref-grid", dest="ref_n", type=int, default=512, help="grid edge of the bounded CPU sample (one step of the reference arm)")
+    ap.add_argument("--ref-fit", default="256,512,1024", help="reference arm: grid edges timed once each for the in-run scaling-law fit")
+    ap.add_argument("--slab-grid", type=int, default=-1, help="also time one G^2 solve split into row slabs over the ranks (0: off; default: 8192 when --gpus > 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep", type=int, default=4, help="frequencies per GPU per step, solved concurrently (one stream each)")
     ap.add_argument("--no-e2e", action="store_true", help="slab mode: skip the host-buffer (end-to-end) repetition of the solve")
@@ -129,6 +135,14 @@ def cpu_reference_solve(n, density, threads=None):
     return dt, f
 
 
+def fit_exponent(samples):
+    """least-squares slope of log t against log N (N = unknowns) over the measured (edge, seconds) samples"""
+    if len(samples) < 2:
+        return math.log(5.5) / math.log(4.0), "survey-time law (x5.5 per 4x unknowns, BASELINE.md §3): fewer than two sizes measured"
+    x = np.log([float(n) * n for n, _ in samples]); y = np.log([t for _, t in samples])
+    return float(np.polyfit(x, y, 1)[0]), "fitted in this run over " + ", ".join(f"{n}^2: {t:.2f} s" for n, t in samples)
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -141,20 +155,27 @@ def reference_arm(args):
         if i >= args.warmup:
             times.append(dt)
     t = float(np.mean(times))
-    # scale the bounded sample to the metric's configuration with the measured direct-solver law of BASELINE.md §3
-    # (x5.5 time per 4x unknowns, i.e. exponent log(5.5)/log(4) = 1.23 in the number of unknowns)
-    expo = math.log(5.5) / math.log(4.0)
+    # the direct solver's scaling law, measured once per size in this run on this box (not part of the K timed steps)
+    samples = []
+    for ne in sorted({int(v) for v in args.ref_fit.split(",") if v.strip()}):
+        samples.append((ne, t) if ne == nref else (ne, cpu_reference_solve(ne, args.density)[0]))
+    expo, how = fit_exponent(samples)
     scale = ((args.n * args.n) / float(nref * nref)) ** expo
     val = 1.0 / (t * scale)
-    sample = (f"sparse direct LU (SciPy SuperLU standing in for Julia \\ / UMFPACK) of the same synthetic TM device at "
-              f"{nref}x{nref}: {t:.2f} s per solve on {cores} host cores; scaled to {args.n}^2 by the measured law t ~ N^{expo:.2f} "
-              f"(BASELINE.md §3) -> {t * scale:.0f} s per solve" + ("; the 4096^2 factorisation itself needs >200 GB of host RAM" if args.n >= 4096 else ""))
+    sample = (f"sparse direct LU (SciPy SuperLU standing in for Julia \\ / UMFPACK) of the same synthetic TM device, SOLVED at "
+              f"{nref}x{nref}: {t:.2f} s per solve on {cores} host cores; extrapolated to {args.n}^2 by t ~ N^{expo:.3f} ({how}) "
+              f"-> {t * scale:.0f} s per solve" + ("; the 4096^2 factorisation itself needs >200 GB of host RAM and ~10 h" if args.n >= 4096 else ""))
+    cfg = workload_config(args)
+    cfg["grid_solved_by_this_arm"] = [nref, nref]
+    cfg["extrapolated_to"] = [args.n, args.n]
     line = {"impl": "reference", "metric": metric_name(args), "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": t * scale * 1e3, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": t * scale * 1e3, "measured_ms_per_step_at_sample_grid": t * 1e3,
+            "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "c128", "data": "synthetic",
-            "config": workload_config(args),
+            "config": cfg,
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                             "sample_seconds_per_solve": t, "sample_grid": [nref, nref]},
+                             "sample_seconds_per_solve": t, "sample_grid": [nref, nref], "fit_exponent": expo,
+                             "fit_samples": [{"grid": [n_, n_], "seconds": t_} for n_, t_ in samples]},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -171,7 +192,8 @@ def workload_config(args):
             "grid": [args.n, args.n],
             "solver": ("BiCGSTAB + shifted-Laplacian multigrid (fp32) / fp64 operator" if args.solver == "bicgstab" or (args.solver == "auto" and args.n * args.n < 2 ** 22) else
                        f"multilevel Krylov (flexible GMRES per level, steps {args.ml_spec or '6,6'}, F cycles) + shifted-Laplacian multigrid (fp32) / fp64 operator"),
-            "l2": "inputs larger than L2: one complex128 vector is 268 MB vs 126 MB L2", "parallelism": f"omega sweep: {args.sweep} frequencies per GPU per step, disjoint frequencies per rank, no collective"}
+            "l2": "inputs larger than L2: one complex128 vector is 268 MB vs 126 MB L2",
+            "parallelism": f"omega sweep: {args.sweep} frequencies per GPU per step, the same frequency set on every rank (independent replicas of the unit of work), no data-path collective"}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -197,8 +219,9 @@ def b200_arm(args):
     d = wl.synthetic_tm_device(fdfd, n, n, density=args.density)
     g = d.grid
     gc = g.as_c()
-    # this rank's slice of the omega sweep: B frequencies, solved concurrently by the library (one stream each)
-    omegas = [2 * math.pi * (200e12 + 0.5e12 * (rank * B + k)) for k in range(B)]
+    # B frequencies per step, solved concurrently by the library (one stream each); every rank gets the SAME set (weak scaling
+    # with identical work per GPU -- the iteration count depends on the frequency)
+    omegas = [2 * math.pi * (200e12 + 0.5e12 * k) for k in range(B)]
     wB = (C.c_double * B)(*omegas)
     opts = fdfd.default_opts(concurrency=args.concurrency or B)
     if args.solver != "auto":
@@ -288,8 +311,20 @@ def b200_arm(args):
 
     ok = all(i["flag"] == 0 and i["relres"] <= 1e-10 for i in infos)
     flags = torch.tensor([1 if ok else 0], device="cuda")
+    per_rank = [{"rank": rank, "seconds": t_res, "iters": [i["iters"] for i in infos], "krylov_ms": [round(i["solve_ms"], 1) for i in infos]}]
     if world > 1:
         dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, per_rank[0])
+        per_rank = gathered
+    slab_rec = None
+    sg = args.slab_grid if args.slab_grid >= 0 else (8192 if world > 1 else 0)
+    if sg > 0:
+        ctx_s = ctx
+        try:
+            slab_rec = slab_record(args, sg, fdfd, ctx_s, stream, rank, world, local)
+        except Exception as e:  # noqa: BLE001 -- the sweep line must survive a failed slab leg
+            slab_rec = {"error": str(e)[-300:]}
     if rank == 0:
         value = world * B * args.steps / t_max
         line = {"metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -298,9 +333,9 @@ def b200_arm(args):
                 "converged": bool(flags.item()),
                 "solve": {"solves_per_step_per_gpu": B, "iters": [i["iters"] for i in infos], "relres_max": max(i["relres"] for i in infos),
                           "krylov_ms": [round(i["solve_ms"], 1) for i in infos], "setup_ms": [round(i["setup_ms"], 1) for i in infos],
-                          "mg_levels": infos[0]["mg_levels"]},
-                "e2e": {"value": world * B * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * N * 16,
-                        "d2h_bytes_per_step": B * 3 * N * 16, "steps": e2e_steps, "clocks": clk_e2e.summary(),
+                          "mg_levels": infos[0]["mg_levels"], "per_rank": per_rank},
+                "e2e": {"value": world * B * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": world * 2 * N * 16,
+                        "d2h_bytes_per_step": world * B * 3 * N * 16, "steps": e2e_steps, "clocks": clk_e2e.summary(),
                         "call_ms": [round(i["total_ms"], 1) for i in e2e_infos], "krylov_ms": [round(i["solve_ms"], 1) for i in e2e_infos]},
                 "gpu_launches": int(launches),
                 "clocks": clk.summary(),
@@ -312,19 +347,25 @@ def b200_arm(args):
                                        "peak": peak, "unit": "GB/s",
                                        "kernels": [dict(k, frac=k["achieved_gbs"] / peak) for k in mg_kernels],
                                        "ms_per_cycle": ms_cycle}}
+        if slab_rec is not None:
+            line["slab"] = slab_rec
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             t_cpu, _ = cpu_reference_solve(args.ref_n, args.density)
-            expo = math.log(5.5) / math.log(4.0)
+            t_half, _ = cpu_reference_solve(args.ref_n // 2, args.density)
+            expo, how = fit_exponent([(args.ref_n // 2, t_half), (args.ref_n, t_cpu)])
             scale = (N / float(args.ref_n ** 2)) ** expo
             line["cpu_baseline"] = {"value": 1.0 / (t_cpu * scale), "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"oracle (SciPy SuperLU direct solve, stand-in for Julia \\/UMFPACK) on the same device at "
-                                              f"{args.ref_n}^2: {t_cpu:.2f} s; scaled to {n}^2 by t ~ N^{expo:.2f} (BASELINE.md §3)",
-                                    "sample_seconds_per_solve": t_cpu}
-        prof = os.path.join(ROOT, "profiles", "r01_k_apply_traffic.json")
+                                    "sample": f"oracle (SciPy SuperLU direct solve, stand-in for Julia \\/UMFPACK) on the same device, SOLVED at "
+                                              f"{args.ref_n}^2: {t_cpu:.2f} s; extrapolated to {n}^2 by t ~ N^{expo:.3f} ({how})",
+                                    "sample_seconds_per_solve": t_cpu, "sample_grid": [args.ref_n, args.ref_n], "fit_exponent": expo}
+        # DRAM bytes per launch of the SAME k_apply instantiation (complex128 in, no fused dot, 4 rows per thread), from the
+        # `ncu --set full` capture of this round (tools/r2_profile.sh; profiles/r02_k_apply_traffic.json says which command)
+        prof = os.path.join(ROOT, "profiles", "r02_k_apply_traffic.json")
         if os.path.exists(prof) and n == 4096:
             try:
                 line["roofline"]["traffic"] = json.load(open(prof))["dram_bytes_per_launch"]
+                line["roofline"]["traffic_source"] = "profiles/r02_k_apply_traffic.json"
             except Exception:
                 pass
         print(json.dumps(line), flush=True)
@@ -332,26 +373,16 @@ def b200_arm(args):
         dist.destroy_process_group()
 
 
-def slab_arm(args):
-    """One grid, row slabs over the ranks (SURVEY §8e second mode): step = one fdfd_solve_driven_slab call on every rank."""
+def slab_run(args, n, fdfd, ctx, stream, rank, world, local, steps, warmup, e2e):
+    """ONE n x n TM solve split into row slabs over the ranks (SURVEY §8e second mode, BASELINE config 5):
+    step = one fdfd_solve_driven_slab call on every rank.  Returns the record on every rank (rank 0's is printed)."""
     import ctypes as C
     import torch
     import torch.distributed as dist
-    import fdfd_jl_b200 as fdfd
     from importlib import import_module
     wl = import_module("fdfd_jl_b200.workloads")
     slab = import_module("fdfd_jl_b200.slab")
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    stream = torch.cuda.Stream()
-    ctx = fdfd.Context(local, stream=stream.cuda_stream)
     comm = slab.SlabComm.nccl(ctx, rank, world)
-    n = args.n
     g0 = fdfd.Grid(0.02, [15, 15], [0.0, n * 0.02], [0.0, n * 0.02])
     y0, nr = slab.slab_rows(g0, world, rank)
     g, omega, eps_rows, src_rows = wl.synthetic_tm_device(fdfd, n, n, density=args.density, rows=(y0, nr))
@@ -362,7 +393,7 @@ def slab_arm(args):
     src_h = torch.from_numpy(np.asfortranarray(src_rows).ravel(order="F").copy()).pin_memory()
     eps_d, src_d = eps_h.cuda(), src_h.cuda()
     fields_d = torch.empty(3 * M, dtype=torch.complex128, device="cuda")
-    fields_h = torch.empty(3 * M, dtype=torch.complex128).pin_memory()
+    fields_h = torch.empty(3 * M, dtype=torch.complex128).pin_memory() if e2e else None
 
     def barrier():
         torch.cuda.synchronize()
@@ -374,18 +405,19 @@ def slab_arm(args):
         info = fdfd.Info()
         code = fdfd.lib().fdfd_solve_driven_slab(ctx.handle, comm.handle, C.byref(gc), omega, fdfd.ptr(e), fdfd.ptr(s_), C.byref(opts),
                                                  fdfd.ptr(f), C.byref(info))
-        fdfd.check(code, ctx.handle)
+        if code not in (0, fdfd._lib.ERR_NOCONV, fdfd._lib.ERR_BREAKDOWN):   # an unconverged solve is reported, not raised: every rank sees the same flag
+            fdfd.check(code, ctx.handle)
         return info.asdict()
 
     infos = []
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step(eps_d.data_ptr(), src_d.data_ptr(), fields_d.data_ptr())
     barrier()
     l0 = ctx.launch_count()
     with ClockSampler(local) as clk:
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for _ in range(args.steps):
+        for _ in range(steps):
             infos.append(step(eps_d.data_ptr(), src_d.data_ptr(), fields_d.data_ptr()))
             stream.synchronize()
         e1.record(stream)
@@ -395,7 +427,7 @@ def slab_arm(args):
     barrier()
     e2 = torch.cuda.Event(enable_timing=True); e3 = torch.cuda.Event(enable_timing=True)
     e2.record(stream)
-    if not args.no_e2e:
+    if e2e:
         step(eps_h.data_ptr(), src_h.data_ptr(), fields_h.data_ptr())
     stream.synchronize()
     e3.record(stream)
@@ -407,25 +439,47 @@ def slab_arm(args):
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     t_max, t_e2e = float(tt[0].item()), float(tt[1].item())
     st = comm.stats()
-    if rank == 0:
-        i0 = infos[-1]
-        line = {"metric": f"solves_per_sec_{n}x{n}_TM_slab_to_1e-10", "value": args.steps / t_max, "unit": UNIT, "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_max / args.steps * 1e3, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
-                "config": {"workload": f"ONE synthetic TM device {n}x{n} (same map family as the sweep workload) split into {world} row slabs of "
-                                       f"{nr} rows; step = setup + BiCGSTAB/multigrid to 1e-10 + H recovery on every slab",
-                           "grid": [n, n], "parallelism": f"y-slabs x{world}: ring halo exchange (ncclSend/Recv) after every stencil-type kernel, "
-                                                          "one 4-double allreduce per dot product, iteration replayed as one CUDA graph",
-                           "l2": "inputs larger than L2"},
-                "converged": bool(ok.item()),
-                "solve": {"iters": [i["iters"] for i in infos], "relres": [i["relres"] for i in infos],
-                          "krylov_ms": [round(i["solve_ms"], 1) for i in infos], "setup_ms": [round(i["setup_ms"], 1) for i in infos],
-                          "mg_levels": i0["mg_levels"], "ms_per_iteration": i0["solve_ms"] / max(1, i0["iters"])},
-                "e2e": None if args.no_e2e else {"value": 1.0 / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * M * 16 * world,
-                                                 "d2h_bytes_per_step": 3 * M * 16 * world, "steps": 1},
-                "gpu_launches": int(launches), "comm_per_rank_captured": st, "clocks": clk.summary()}
-        print(json.dumps(line), flush=True)
+    i0 = infos[-1]
+    rec = {"metric": f"solves_per_sec_{n}x{n}_TM_slab_to_1e-10", "value": steps / t_max, "unit": UNIT, "n_gpus": world,
+           "steps": steps, "warmup": warmup, "ms_per_step": t_max / steps * 1e3, "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+           "config": {"workload": f"ONE synthetic TM device {n}x{n} (same map family as the sweep workload) split into {world} row slabs of "
+                                  f"{nr} rows; step = setup + BiCGSTAB/multigrid to 1e-10 + H recovery on every slab",
+                      "grid": [n, n], "parallelism": f"y-slabs x{world}: ring halo exchange after every stencil-type kernel, "
+                                                     "one 4-double allreduce per dot product, iteration replayed as one CUDA graph",
+                      "l2": "inputs larger than L2"},
+           "converged": bool(ok.item()),
+           "solve": {"iters": [i["iters"] for i in infos], "relres": [i["relres"] for i in infos],
+                     "krylov_ms": [round(i["solve_ms"], 1) for i in infos], "setup_ms": [round(i["setup_ms"], 1) for i in infos],
+                     "mg_levels": i0["mg_levels"], "ms_per_iteration": i0["solve_ms"] / max(1, i0["iters"])},
+           "e2e": None if not e2e else {"value": 1.0 / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * M * 16 * world,
+                                        "d2h_bytes_per_step": 3 * M * 16 * world, "steps": 1},
+           "gpu_launches": int(launches), "comm_per_rank_captured": st, "clocks": clk.summary()}
     comm.close()
+    return rec
+
+
+def slab_record(args, n, fdfd, ctx, stream, rank, world, local):
+    """the slab strong-scaling datum carried by the sweep line: one solve, no warm-up repetition (a solve is tens of seconds)"""
+    r = slab_run(args, n, fdfd, ctx, stream, rank, world, local, steps=1, warmup=0, e2e=False)
+    return {k: r[k] for k in ("metric", "value", "unit", "n_gpus", "ms_per_step", "scaling", "converged", "solve", "config", "comm_per_rank_captured", "gpu_launches")}
+
+
+def slab_arm(args):
+    import torch
+    import torch.distributed as dist
+    import fdfd_jl_b200 as fdfd
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.Stream()
+    ctx = fdfd.Context(local, stream=stream.cuda_stream)
+    rec = slab_run(args, args.n, fdfd, ctx, stream, rank, world, local, steps=args.steps, warmup=args.warmup, e2e=not args.no_e2e)
+    if rank == 0:
+        print(json.dumps(rec), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

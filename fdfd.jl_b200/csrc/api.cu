@@ -313,6 +313,28 @@ extern "C" int fdfd_solve_driven(fdfd_ctx* ctx, const fdfd_grid_t* g, int pol, i
   }
   std::vector<fdfd_info_t> infos(n_omega);
   std::vector<int> status(n_omega, FDFD_OK);
+  // host inputs are staged into HBM ONCE per call (the reference re-reads d.eps_r / d.src for every frequency, driven.jl:21,36):
+  // every frequency's problem then copies device to device, and the call moves 2 N (or (1 + n_omega) N) complex numbers over
+  // PCIe instead of 2 N n_omega.  The staging runs on the caller's stream, which the worker streams are ordered against below.
+  DevBuf<c128> eps_stage, src_stage;
+  if (n_omega > 1) {
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (!fdfd_is_device_ptr(eps_r)) {
+      CUDA_TRY(ctx, eps_stage.alloc(N));
+      FDFD_TRY(fdfd_copy_in(ctx, eps_stage.p, eps_r, N * sizeof(c128)));
+      eps_r = reinterpret_cast<const fdfd_c128*>(eps_stage.p);
+    }
+    if (!fdfd_is_device_ptr(src)) {
+      const size_t cnt = (size_t)N * (src_per_omega ? n_omega : 1);
+      CUDA_TRY(ctx, src_stage.alloc(cnt));
+      FDFD_TRY(fdfd_copy_in(ctx, src_stage.p, src, cnt * sizeof(c128)));
+      src = reinterpret_cast<const fdfd_c128*>(src_stage.p);
+    }
+    // workers run on private streams: the caller's stream (which may carry the producers of device-resident eps_r / src, and
+    // carries the staging copies above) must be drained before they start; every worker synchronises its own stream before it
+    // returns, so the outputs are complete when the call returns
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   if (nworkers == 1) {
     for (int i = 0; i < n_omega; ++i) {
       status[i] = solve_one_omega(ctx, g, pol, omega[i], eps_r, src + (src_per_omega ? (size_t)i * N : 0), &o,
@@ -327,7 +349,7 @@ extern "C" int fdfd_solve_driven(fdfd_ctx* ctx, const fdfd_grid_t* g, int pol, i
     for (int wkr = 0; wkr < nworkers; ++wkr) {
       th.emplace_back([&, wkr]() {
         fdfd_ctx* sub = nullptr;
-        if (fdfd_ctx_create(ctx->device, nullptr, &sub) != FDFD_OK) { errs[wkr] = fdfd_last_error(nullptr); return; }
+        if (fdfd_ctx_create(ctx->device, nullptr, &sub) != FDFD_OK) { errs[wkr] = "fdfd_solve_driven: could not create a worker context (stream)"; return; }
         for (int i = next.fetch_add(1); i < n_omega; i = next.fetch_add(1)) {
           status[i] = solve_one_omega(sub, g, pol, omega[i], eps_r, src + (src_per_omega ? (size_t)i * N : 0), &o,
                                       fields + (size_t)i * 3 * N, &infos[i]);

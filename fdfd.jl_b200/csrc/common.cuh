@@ -123,6 +123,7 @@ template <typename T> struct DevBuf {
 };
 
 // copy count elements from a caller pointer (host or device) into device memory, async on stream
+bool fdfd_is_device_ptr(const void* p);
 int fdfd_copy_in(fdfd_ctx* ctx, void* dst_dev, const void* src_any, size_t bytes);
 int fdfd_copy_out(fdfd_ctx* ctx, void* dst_any, const void* src_dev, size_t bytes);
 

@@ -146,7 +146,7 @@ extern "C" void fdfd_default_opts(fdfd_solve_opts_t* o) {
   o->ml_spec = 0;
 }
 
-static bool is_device_ptr(const void* p) {
+bool fdfd_is_device_ptr(const void* p) {
   cudaPointerAttributes a;
   cudaError_t e = cudaPointerGetAttributes(&a, p);
   if (e != cudaSuccess) { cudaGetLastError(); return false; }
@@ -155,7 +155,7 @@ static bool is_device_ptr(const void* p) {
 
 int fdfd_copy_in(fdfd_ctx* ctx, void* dst_dev, const void* src_any, size_t bytes) {
   if (bytes == 0) return FDFD_OK;
-  cudaMemcpyKind k = is_device_ptr(src_any) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  cudaMemcpyKind k = fdfd_is_device_ptr(src_any) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   CUDA_TRY(ctx, cudaMemcpyAsync(dst_dev, src_any, bytes, k, ctx->stream));
   // pageable host memory: the copy is staged synchronously by the runtime; pinned: truly async.
   // Either way the caller's buffer must stay valid until we sync, which every API call does before returning.
@@ -164,7 +164,7 @@ int fdfd_copy_in(fdfd_ctx* ctx, void* dst_dev, const void* src_any, size_t bytes
 
 int fdfd_copy_out(fdfd_ctx* ctx, void* dst_any, const void* src_dev, size_t bytes) {
   if (bytes == 0) return FDFD_OK;
-  cudaMemcpyKind k = is_device_ptr(dst_any) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  cudaMemcpyKind k = fdfd_is_device_ptr(dst_any) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   CUDA_TRY(ctx, cudaMemcpyAsync(dst_any, src_dev, bytes, k, ctx->stream));
   return FDFD_OK;
 }

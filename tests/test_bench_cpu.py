@@ -20,7 +20,7 @@ def _run(*args, timeout=600):
 
 
 def test_reference_arm_prints_the_contract_line():
-    p = _run("--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-grid", "128")
+    p = _run("--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-grid", "128", "--ref-fit", "64,128,192")
     assert p.returncode == 0, p.stderr[-2000:]
     lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
@@ -29,7 +29,10 @@ def test_reference_arm_prints_the_contract_line():
     assert z["n_gpus"] == 1 and z["steps"] == 1 and z["warmup"] == 0 and z["higher_is_better"] is True
     assert z["value"] > 0 and z["ms_per_step"] > 0 and z["vs_baseline"] is None and z["dtype"] == "c128" and z["data"] == "synthetic"
     assert "workload" in z["config"] and "model" not in z["config"]
+    # the arm says which grid it really solved and how it extrapolated (round-1 finding: a 512^2 run labelled 4096^2)
+    assert z["config"]["grid_solved_by_this_arm"] == [128, 128] and z["config"]["extrapolated_to"] == [4096, 4096]
     cb = z["cpu_baseline"]
+    assert len(cb["fit_samples"]) == 3 and 0.8 < cb["fit_exponent"] < 2.5
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == z["value"] and cb["sample"]
     e = z["e2e"]
     assert e["value"] == z["value"] and e["unit"] == z["unit"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
