@@ -242,6 +242,10 @@ def get_modes(d: Device, pol, omega, neff, nmodes, pt, slicenormal, slicewidth):
         iy = iy + np.arange(-M, M + 1); h = dy(g)
     else:
         ix = ix + np.arange(-M, M + 1); h = dx(g)
+    # Julia throws a BoundsError when the slice leaves the grid (device.jl:133-146); NumPy would wrap negative indices silently
+    Nx, Ny = g.N
+    if np.min(ix) < 1 or np.max(ix) > Nx or np.min(iy) < 1 or np.max(iy) > Ny:
+        raise IndexError(f"mode slice x in [{np.min(ix)}, {np.max(ix)}], y in [{np.min(iy)}, {np.max(iy)}] leaves the {Nx} x {Ny} grid")
     eps_slice = d.eps_r[ix - 1, iy - 1]
     beta, vec = eigenmode_1d(eps_slice, h, g.L0, omega, pol, neff, nmodes)
     return beta, vec, ix - 1, iy - 1

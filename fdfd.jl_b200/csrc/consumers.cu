@@ -64,6 +64,8 @@ extern "C" int fdfd_problem_flux_x(fdfd_problem* P, double center_x, double cent
     if (std::fabs(xc - center_x) <= dx / 2 * (1 + 1e-9)) { xi = i; break; }
   }
   ARG_CHECK(ctx, xi >= 0, "no x-centre within dx/2 of center_x");
+  // flux.jl:40-42 indexes the column after xi: on the last column the reference throws, a periodic wrap to column 0 would be silent
+  ARG_CHECK(ctx, xi + 1 < g.Nx, "the flux plane sits on the last grid column: column xi + 1 does not exist (flux.jl:40-42)");
   int64_t j0 = g.Ny, j1 = 0;
   for (int64_t j = 0; j < g.Ny; ++j) {
     const double yc = g.y0 + dy * (0.5 + (double)j);

@@ -13,6 +13,7 @@
 // allreduce, the Hessenberg matrix lives on the host (identical on every rank: the allreduce is bit-reproducible).
 //
 // GPU tests: tests/test_gpu_slab_multi.py (1 / 2 / 4 slabs against the single-GPU solves and the oracle).
+#include "arnoldi.cuh"
 #include "comm.cuh"
 #include "krylov.cuh"
 #include "reduce.cuh"
@@ -24,7 +25,7 @@
 using cd = std::complex<double>;
 
 void slab_depth(const fdfd_grid_t& g, double omega, const MGParams& prm, int64_t nyl, int* nlev_out, int* ka_out);
-bool hess_eig(int n, std::vector<cd> H, std::vector<cd>& evals, std::vector<cd>& evecs);
+
 double which_key(int which, cd nu);
 
 namespace {
@@ -397,12 +398,13 @@ int eigenfrequency_slab(fdfd_ctx* ctx, fdfd_comm* comm, const fdfd_grid_t* g, do
   const double t0 = wall_ms();
   fdfd_solve_opts_t o;
   if (opts) o = *opts; else fdfd_default_opts(&o);
-  const double tol_eig = 1e-10;            // Ritz residual |h_{m+1,m} y_m| <= tol_eig |nu|   (as eigen.cu)
-  o.tol = std::min(o.tol, 1e-11);
+  o.tol = std::min(o.tol, 1e-11);          // inner solves; Ritz residual |b^T y| <= 10 o.tol |nu|   (as eigen.cu)
+  const double tol_eig = 10.0 * o.tol;
   if (ncv <= 0) ncv = std::max(20, 2 * nev + 1);
   const int64_t Nglob = g->Nx * g->Ny;
   ARG_CHECK(ctx, nev + 2 <= Nglob, "nev too large for the grid");
-  const int mcap = (int)std::min<int64_t>(std::max(ncv, 400), Nglob - 1);
+  ncv = (int)std::min<int64_t>(std::max(ncv, nev + 2), Nglob - 1);
+  const int max_steps = std::max(300, 30 * nev) + ncv;
   const double eps0 = kEps0 * g->L0, mu0 = kMu0 * g->L0;
   const cd sigma(-omega0 * omega0 * mu0 * eps0, 0);   // eigen.jl:86
 
@@ -411,92 +413,82 @@ int eigenfrequency_slab(fdfd_ctx* ctx, fdfd_comm* comm, const fdfd_grid_t* g, do
   cudaStream_t st = ctx->stream;
   const int nb = S.w.nvec_blocks;
   const int64_t Nl = S.Nloc, own = S.nyl * S.Nx;
-  std::vector<DevBuf<c128>> V;
-  auto add_vec = [&]() -> int {
-    V.emplace_back();
-    if (V.back().alloc(Nl) != cudaSuccess) { cudaGetLastError(); fdfd_set_error(ctx, "out of device memory for the Arnoldi basis"); return FDFD_ERR_ALLOC; }
+  std::vector<DevBuf<c128>> V;   // Arnoldi basis, sharded like every vector (owned rows + zero halo rows); at most ncv + 1 vectors
+  auto ensure = [&](int j) -> int {
+    while ((int)V.size() <= j) {
+      V.emplace_back();
+      if (V.back().alloc(Nl) != cudaSuccess) { cudaGetLastError(); fdfd_set_error(ctx, "out of device memory for the Arnoldi basis"); return FDFD_ERR_ALLOC; }
+    }
     return FDFD_OK;
   };
   DevBuf<c128> wv; DevBuf<double> parts;
   CUDA_TRY(ctx, wv.alloc(Nl)); CUDA_TRY(ctx, parts.alloc((size_t)nb * 4));
-  const int ld = mcap + 1;
-  std::vector<cd> Hm_full((size_t)ld * mcap, cd(0, 0));
-
-  // v1: pseudo-random on the owned rows, zero halo rows, unit global norm
-  FDFD_TRY(add_vec());
-  CUDA_TRY(ctx, cudaMemsetAsync(wv.p, 0, Nl * sizeof(c128), st));
-  k_seed_rows<<<nb, 256, 0, st>>>(S.Nx, S.nyl, S.y0, wv.p + S.H * S.Nx, 20260101); KLAUNCH(ctx);
-  cd nrm2;
-  FDFD_TRY(slab_dot(S, parts, wv.p, wv.p, &nrm2));
-  k_scale_real<<<nb, 256, 0, st>>>(Nl, 1.0 / std::sqrt(nrm2.real()), wv.p, V[0].p); KLAUNCH(ctx);
-
-  int m = 0, inner_its = 0;
+  int inner_its = 0;
   const int64_t launches0 = ctx->launches;
   double inner_ms = 0;
-  std::vector<cd> evals, evecs;
-  std::vector<int> pick;
-  bool converged = false;
-  while (m < mcap) {
-    // w = OP v_m:  (L/mu0 + w0^2 eps0 eps_r) y = eps_r v / mu0   -- the driven TM operator at w0
-    k_eps_scale<<<nb, 256, 0, st>>>(Nl, 1.0 / mu0, S.ops[0]->eps.p, V[m].p, S.w.b.p); KLAUNCH(ctx);   // v has zero halo rows => so has b
+
+  // the projected matrix lives on the host of every rank; it is identical everywhere because the dot products come out of the
+  // bit-reproducible allreduce, so every rank takes the same restart decisions (no extra synchronisation)
+  ArnoldiOps ops;
+  ops.op_apply = [&](int j) -> int {
+    // w = OP v_j:  (L/mu0 + w0^2 eps0 eps_r) y = eps_r v / mu0   -- the driven TM operator at w0
+    k_eps_scale<<<nb, 256, 0, st>>>(Nl, 1.0 / mu0, S.ops[0]->eps.p, V[j].p, S.w.b.p); KLAUNCH(ctx);   // v has zero halo rows => so has b
     fdfd_info_t inf{};
     FDFD_TRY(S.solve(&inf));
-    if (inf.flag != FDFD_OK) { fdfd_set_error(ctx, "fdfd_eigenfrequency_slab: inner solve %d failed (flag %d, relres %.2e)", m, inf.flag, inf.relres); return inf.flag; }
+    if (inf.flag != FDFD_OK) { fdfd_set_error(ctx, "fdfd_eigenfrequency_slab: inner solve %d failed (flag %d, relres %.2e)", j, inf.flag, inf.relres); return inf.flag; }
     inner_its += inf.iters; inner_ms += inf.solve_ms;
     // the solution's halo rows hold copies of the neighbours' rows: basis vectors keep zero halo rows
     CUDA_TRY(ctx, cudaMemsetAsync(wv.p, 0, Nl * sizeof(c128), st));
     CUDA_TRY(ctx, cudaMemcpyAsync(wv.p + S.H * S.Nx, S.w.x.p + S.H * S.Nx, own * sizeof(c128), cudaMemcpyDeviceToDevice, st));
-    for (int pass = 0; pass < 2; ++pass) {   // Gram-Schmidt twice
-      for (int i = 0; i <= m; ++i) {
-        cd h;
-        FDFD_TRY(slab_dot(S, parts, V[i].p, wv.p, &h));
-        k_axpy_m<<<nb, 256, 0, st>>>(Nl, to_c128(h), V[i].p, wv.p); KLAUNCH(ctx);
-        Hm_full[(size_t)m * ld + i] += h;
-      }
+    return FDFD_OK;
+  };
+  ops.dot_v_w = [&](int i, cd* h) -> int { return slab_dot(S, parts, V[i].p, wv.p, h); };
+  ops.axpy_w = [&](int i, cd h) -> int { k_axpy_m<<<nb, 256, 0, st>>>(Nl, to_c128(h), V[i].p, wv.p); KLAUNCH(ctx); return FDFD_OK; };
+  ops.norm_w = [&](double* nrm) -> int {
+    cd n2;
+    FDFD_TRY(slab_dot(S, parts, wv.p, wv.p, &n2));
+    *nrm = std::sqrt(std::max(0.0, n2.real()));
+    return FDFD_OK;
+  };
+  ops.set_v = [&](int j, double sc) -> int {
+    FDFD_TRY(ensure(j));
+    k_scale_real<<<nb, 256, 0, st>>>(Nl, sc, wv.p, V[j].p); KLAUNCH(ctx);
+    return FDFD_OK;
+  };
+  ops.random_w = [&](int seed) -> int {   // pseudo-random on the owned rows (a function of the GLOBAL row), zero halo rows
+    CUDA_TRY(ctx, cudaMemsetAsync(wv.p, 0, Nl * sizeof(c128), st));
+    k_seed_rows<<<nb, 256, 0, st>>>(S.Nx, S.nyl, S.y0, wv.p + S.H * S.Nx, 20260101ull + 7919ull * (uint64_t)seed); KLAUNCH(ctx);
+    return FDFD_OK;
+  };
+  ops.rotate_basis = [&](int m, int k, const std::vector<cd>& Q) -> int {
+    std::vector<DevBuf<c128>> T(k);
+    for (int i = 0; i < k; ++i) {
+      if (T[i].alloc(Nl) != cudaSuccess) { cudaGetLastError(); fdfd_set_error(ctx, "out of device memory for the thick restart"); return FDFD_ERR_ALLOC; }
+      for (int j = 0; j < m; ++j) { k_axpy_acc<<<nb, 256, 0, st>>>(Nl, to_c128(Q[(size_t)i * m + j]), V[j].p, T[i].p, j == 0); KLAUNCH(ctx); }
     }
-    FDFD_TRY(slab_dot(S, parts, wv.p, wv.p, &nrm2));
-    const double hnext = std::sqrt(std::max(0.0, nrm2.real()));
-    Hm_full[(size_t)m * ld + (m + 1)] = hnext;
-    ++m;
-    const bool breakdown = hnext <= 1e-14 * std::abs(Hm_full[(size_t)(m - 1) * ld + (m - 1)]);
-    if (!breakdown) {
-      FDFD_TRY(add_vec());
-      k_scale_real<<<nb, 256, 0, st>>>(Nl, 1.0 / hnext, wv.p, V[m].p); KLAUNCH(ctx);
-    }
-    if (m >= nev + 2 || breakdown || m == mcap) {
-      std::vector<cd> Hm((size_t)m * m);
-      for (int j = 0; j < m; ++j) for (int i = 0; i < m; ++i) Hm[(size_t)j * m + i] = Hm_full[(size_t)j * ld + i];
-      if (!hess_eig(m, Hm, evals, evecs)) { fdfd_set_error(ctx, "fdfd_eigenfrequency_slab: Hessenberg QR did not converge"); return FDFD_ERR_NOCONV; }
-      std::vector<int> idx(m);
-      for (int i = 0; i < m; ++i) idx[i] = i;
-      std::sort(idx.begin(), idx.end(), [&](int a, int b) { return which_key(which, evals[a]) > which_key(which, evals[b]); });
-      pick.assign(idx.begin(), idx.begin() + std::min(nev, m));
-      bool ok = (int)pick.size() == nev;
-      for (int k : pick) {
-        const double res = hnext * std::abs(evecs[(size_t)k * m + (m - 1)]);
-        if (!(res <= tol_eig * std::abs(evals[k]))) ok = false;
-      }
-      if (o.verbose) fprintf(stderr, "[fdfd_b200] slab arnoldi m=%d converged=%d\n", m, (int)ok);
-      if (ok || breakdown) { converged = true; break; }
-    }
-  }
-  if (!converged) { fdfd_set_error(ctx, "fdfd_eigenfrequency_slab: %d Ritz pairs did not converge within %d Arnoldi steps", nev, m); return FDFD_ERR_NOCONV; }
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    std::swap(V[k], V[m]);
+    for (int i = 0; i < k; ++i) std::swap(V[i], T[i]);
+    return FDFD_OK;
+  };
+  ArnoldiResult R;
+  FDFD_TRY(krylov_schur(ctx, ops, nev, ncv, which, tol_eig, max_steps, o.verbose != 0, R));
+  const int m = R.m;
 
   DevBuf<c128> ez, f3;
   CUDA_TRY(ctx, ez.alloc(Nl));
   for (int e = 0; e < nev; ++e) {
-    const int k = pick[e];
-    const cd lam = sigma + 1.0 / evals[k];
+    const cd lam = sigma + 1.0 / R.nu[e];
     const cd om = std::sqrt(-lam / mu0 / eps0);   // eigen.jl:87
     omega_out[e].re = om.real(); omega_out[e].im = om.imag();
     if (!fields_rows) continue;
-    for (int i = 0; i < m; ++i) { k_axpy_acc<<<nb, 256, 0, st>>>(Nl, to_c128(evecs[(size_t)k * m + i]), V[i].p, ez.p, i == 0); KLAUNCH(ctx); }
+    for (int i = 0; i < m; ++i) { k_axpy_acc<<<nb, 256, 0, st>>>(Nl, to_c128(R.Y[(size_t)e * m + i]), V[i].p, ez.p, i == 0); KLAUNCH(ctx); }
     FDFD_TRY(S.fields_out(0, ez.p, 1, om, fields_rows + (size_t)e * 3 * own, f3));   // H from FORWARD differences (eigen.jl:90-91)
   }
   if (info) {
     std::memset(info, 0, sizeof(*info));
     info->iters = inner_its; info->flag = FDFD_OK; info->relres = o.tol; info->solve_ms = inner_ms;
-    info->setup_ms = S.setup_ms; info->launches = ctx->launches - launches0; info->restarts = m;   // restarts := Arnoldi steps
+    info->setup_ms = S.setup_ms; info->launches = ctx->launches - launches0; info->restarts = R.steps;   // restarts := Arnoldi steps (operator applications)
     info->mg_levels = S.ka >= 1 ? S.mgcs[0]->levels() : S.nlev;
     info->total_ms = wall_ms() - t0;
   }

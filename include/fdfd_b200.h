@@ -290,6 +290,14 @@ int fdfd_debug_sell_spmv(int64_t n, const int64_t* colptr, const int64_t* rowval
 /* host-only test hook (no GPU needed): the small dense complex Hessenberg eigen-solver behind the Ritz pairs of
  * fdfd_eigenfrequency.  H, evecs: column-major n x n; evals: n. */
 int fdfd_debug_hess_eig(int n, const fdfd_c128* H, fdfd_c128* evals, fdfd_c128* evecs);
+/* host-only test hooks (no GPU needed) of the Krylov-Schur driver behind fdfd_eigenfrequency[_slab] (csrc/arnoldi.cu; stands
+ * where Arpack's implicitly restarted Arnoldi stands, eigen.jl:86,104): the eigen-solver of a general small matrix (the projected
+ * matrix is no longer Hessenberg after a thick restart), and the whole loop -- expansion to ncv, Ritz test |b^T y| <= tol |nu|,
+ * thick restart, invariant-subspace handling -- on a dense n x n operator OP (column major) with host vectors.
+ * `which` = FDFD_WHICH_* on OP's spectrum; out_nu[nev]; out_vecs (may be NULL): nev x n Ritz vectors. */
+int fdfd_debug_general_eig(int n, const fdfd_c128* A, fdfd_c128* evals, fdfd_c128* evecs);
+int fdfd_debug_krylov_schur(int n, const fdfd_c128* OP, int nev, int ncv, int which, double tol, int max_steps,
+                            fdfd_c128* out_nu, fdfd_c128* out_vecs, int* steps, int* restarts);
 
 /* host-only test hooks of FDFD_SOLVER_MLKRYLOV (no GPU needed): the one-thread least-squares solve of the (k+1) x k
  * Hessenberg system min || beta e1 - H y || (H column-major, ld = k+1), and the grid transfers between a fine (nx,ny) grid

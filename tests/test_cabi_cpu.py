@@ -81,6 +81,69 @@ def test_hessenberg_eigensolver_host(fdfd):
             assert np.linalg.norm(H @ vec[:, k] - ev[k] * vec[:, k]) < 1e-10 * max(1, abs(ref).max())
 
 
+def test_general_eig_host(fdfd):
+    """eigen-solver of a general small matrix (Householder -> Hessenberg -> shifted QR): what the Ritz pairs come from after a thick restart"""
+    import numpy as np
+    rng = np.random.default_rng(11)
+    for n in (1, 2, 3, 9, 41):
+        A = np.asfortranarray(rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))
+        ev = np.empty(n, complex); vec = np.empty((n, n), complex, order="F")
+        assert fdfd.lib().fdfd_debug_general_eig(n, fdfd.ptr(A), fdfd.ptr(ev), fdfd.ptr(vec)) == 0
+        ref = np.linalg.eigvals(A)
+        assert max(min(abs(e - ref)) for e in ev) < 1e-10 * max(1, abs(ref).max())
+        for k in range(n):
+            assert np.linalg.norm(A @ vec[:, k] - ev[k] * vec[:, k]) < 1e-9 * max(1, abs(ref).max())
+
+
+def test_krylov_schur_host(fdfd):
+    """the Krylov-Schur loop of fdfd_eigenfrequency (thick restarts keep the basis at ncv + 1 vectors like Arpack, eigen.jl:86) on dense
+    operators with host vectors: non-normal spectrum that needs several restarts, a degenerate pair (the ring resonator's case), every
+    `which`, and an operator of rank 3 whose Krylov space closes after 3 steps (invariant-subspace restart)"""
+    import numpy as np
+    L = fdfd.lib()
+    rng = np.random.default_rng(5)
+
+    def run(OP, nev, ncv, which, tol=1e-12, max_steps=2000):
+        n = OP.shape[0]
+        nu = np.empty(nev, complex); vec = np.empty((n, nev), complex, order="F")
+        steps, restarts = ctypes.c_int32(), ctypes.c_int32()
+        code = L.fdfd_debug_krylov_schur(n, fdfd.ptr(np.asfortranarray(OP)), nev, ncv, which, tol, max_steps, fdfd.ptr(nu), fdfd.ptr(vec),
+                                         ctypes.byref(steps), ctypes.byref(restarts))
+        return code, nu, vec, steps.value, restarts.value
+
+    n = 300
+    X = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    lam = np.concatenate([[5.0, 4.5 + 1j, 4.5 + 1j, -4.2j, 3.9, -3.7], 2.0 * (rng.random(n - 6) - 0.5) + 1.5j * (rng.random(n - 6) - 0.5)])
+    OP = X @ np.diag(lam) @ np.linalg.inv(X)
+    code, nu, vec, steps, restarts = run(OP, 6, 14, 0)
+    assert code == 0 and restarts >= 1                       # 14 vectors are not enough without restarting
+    assert np.allclose(sorted(abs(nu))[::-1], sorted(abs(lam[:6]))[::-1], rtol=1e-9)
+    for k in range(6):
+        v = vec[:, k]
+        assert np.linalg.norm(OP @ v - nu[k] * v) <= 1e-8 * abs(nu[k]) * np.linalg.norm(v)
+    # every `which` picks the matching end of the spectrum
+    keys = {0: abs(lam), 1: lam.real, 2: -lam.real, 3: lam.imag, 4: -lam.imag}
+    for which, key in keys.items():
+        code, nu, _, _, _ = run(OP, 2, 20, which, tol=1e-10)
+        want = lam[np.argsort(-key)[:2]]
+        assert code == 0
+        for z in nu:
+            assert min(abs(z - want)) <= 1e-7 * max(1.0, abs(z)), (which, nu, want)
+    # rank-3 operator: the Krylov space is exhausted after 3-4 steps; the two nonzero-eigenvalue pairs asked for are exact
+    U = rng.standard_normal((40, 3)) + 1j * rng.standard_normal((40, 3))
+    Wt = rng.standard_normal((3, 40)) + 1j * rng.standard_normal((3, 40))
+    OP3 = U @ Wt
+    code, nu, _, steps, _ = run(OP3, 2, 12, 0, tol=1e-10)
+    ref = np.linalg.eigvals(Wt @ U)
+    ref = ref[np.argsort(-abs(ref))]
+    assert code == 0 and steps <= 13
+    for z, r in zip(sorted(nu, key=lambda t: -abs(t)), ref[:2]):
+        assert abs(z - r) <= 1e-8 * abs(r)
+    # an unreachable tolerance ends in FDFD_ERR_NOCONV, not in an unbounded basis
+    code, *_ = run(OP + 1e-3 * rng.standard_normal((n, n)), 6, 9, 0, tol=1e-30, max_steps=60)
+    assert code == 3
+
+
 def test_mlkrylov_least_squares_core_host(fdfd):
     """the one-thread Givens least-squares solve of the multilevel Krylov solver (csrc/mlkrylov.cu), run on the host"""
     import numpy as np

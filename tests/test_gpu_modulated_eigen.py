@@ -131,3 +131,45 @@ def test_eigenfrequency_ring_matches_committed_fixture(fdfd, pol):
     d, _, _, _ = _ring(fdfd, 0.02)
     om, _ = fdfd.eigenfrequency(d, fdfd.TM if pol == "TM" else fdfd.TE, 4, which="LM")
     assert _match(om, ref) <= EIG_TOL
+
+
+def _config4():
+    import json
+    import os
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "eig_config4.json")))
+
+
+@pytest.mark.parametrize("pol", ["TM", "TE"])
+def test_config4_ring_400_ten_modes(fdfd, pol):
+    """BASELINE config 4 as stated: eigenfrequency() of the notebook ring (cell 31) at 400 x 400, the 10 modes nearest 200 THz
+    (`which = :LM` on the shift-inverted spectrum, eigen.jl:86,104), against the committed oracle values (tests/golden/eig_config4.json,
+    12 stored so that a degenerate pair at the cut cannot mismatch).  ncv is Arpack's default max(20, 2 nev + 1) = 21: ten wanted pairs
+    (whispering-gallery modes with Q up to 2e6 next to Q ~ 7 leaky ones, two degenerate pairs) do not converge in 21 Arnoldi steps, so
+    the Krylov-Schur restarts of csrc/arnoldi.cu are exercised and the basis stays at 22 vectors."""
+    ref = [complex(a, b) for a, b in _config4()[f"ring_{pol}_400"]]
+    d, _, _, _ = _ring(fdfd, 0.01)
+    assert d.grid.N == (400, 400)
+    om, fields = fdfd.eigenfrequency(d, fdfd.TM if pol == "TM" else fdfd.TE, 10, which="LM")
+    assert len(om) == 10 and _match(om, ref) <= EIG_TOL
+    assert fields[0].info["restarts"] > 21          # Arnoldi steps (operator applications): more than one basis' worth
+    for f in fields:
+        assert abs(np.linalg.norm(f.data[:, :, 0]) - 1) < 1e-8
+
+
+def test_config4_photonic_crystal_cavity_ten_modes(fdfd):
+    """BASELINE config 4, second device: an L3-type cavity (three rods removed from an 11 x 9 square lattice of eps = 12.25 rods,
+    a = 0.5 um, r = 0.1 um; 256 x 224 grid), TM, the 10 modes nearest 200 THz -- the cavity mode at 191 THz (Q 1e4) and band-edge modes"""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)           # the generator of the fixture builds the permittivity map for the test too
+    phc_cavity_eps = mg.phc_cavity_eps
+    ref = [complex(a, b) for a, b in _config4()["phc_TM"]]
+    gargs = (0.025, [15, 15], [-3.2, 3.2], [-2.8, 2.8])
+    g, go = fdfd.Grid(*gargs), O.Grid2D(*gargs)
+    d = fdfd.Device(g, 2 * math.pi * 200e12)
+    d.eps_r = phc_cavity_eps(go)
+    assert g.N == (256, 224)
+    om, _ = fdfd.eigenfrequency(d, fdfd.TM, 10, which="LM")
+    assert _match(om, ref) <= EIG_TOL
