@@ -186,7 +186,7 @@ def _run_threads(nslabs, devices, work):
             raise e
 
 
-# ---- slab-sharded modulated / eigenfrequency solves (csrc/slab_multi.cu; written without GPU access, see its header) ----
+# ---- slab-sharded modulated / eigenfrequency solves (csrc/slab_multi.cu) ----
 def solve_modulated_slab_rows(grid, omega, Omega, nsidebands, sharedpml, eps_rows, deps_rows, src_rows, comm: SlabComm,
                               ctx: Context, **kw):
     """This rank's rows of solve(d::ModulatedDevice) (modulation.jl:35-119): returns fields (Nx, nrows, 3, nf), sideband
