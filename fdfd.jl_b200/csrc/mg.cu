@@ -709,7 +709,7 @@ constexpr int kLineMaxK = 10;   // segments are at most 640 points long
 template <typename T>
 __global__ void k_lines2(int64_t nx, int64_t ny, int npx, YS ys, LineSeg sy, LineSeg sx, const cplx<T>* __restrict__ mult_y,
                          const cplx<T>* __restrict__ mult_x, const cplx<T>* __restrict__ rxs, const cplx<T>* __restrict__ rys,
-                         cplx<T>* __restrict__ out, T wl, int blk_off, const int* __restrict__ done) {
+                         cplx<T>* __restrict__ out, T wl, int blk_off, unsigned long long* __restrict__ slots, const int* __restrict__ done) {
   if (done && *done) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nby = 2 * npx * sy.nseg;
@@ -756,13 +756,31 @@ __global__ void k_lines2(int64_t nx, int64_t ny, int npx, YS ys, LineSeg sy, Lin
   // corners (strip column AND strip row): the stretched operator is anisotropic in both directions there, so they take the
   // mean of their y-line and their x-line update (both from the same residual).  Measured (tools/gpu_mgdiag.py, 512^2):
   // with x-lines only in the corners the cycle's asymptotic factor is 0.955 and two sweeps per level diverge; with the
-  // mean it is 0.45 and BiCGSTAB needs 92 instead of 167 iterations.  The two updates of a corner point come from different
-  // CTAs, so y-lines and x-lines are two launches (blk_off) -- stream order keeps the sum deterministic.
+  // mean it is 0.45 and BiCGSTAB needs 92 instead of 167 iterations.
+  // The two updates of a corner point come from different CTAs.  fp32: ONE launch -- the CTAs meet in a 64-bit slot per corner
+  // point: whoever arrives first parks its update there with an atomic exchange, the second finds it, adds
+  // u += w (y-update + x-update) in that fixed order (bit-reproducible whatever the arrival order, unlike two atomic adds) and
+  // re-arms the slot.  fp64 (no 128-bit exchange): slots == NULL, y-lines and x-lines are two launches (blk_off).
   const bool corner = ymode ? ys_in(ys, gi) : in_strip(gi, nx, npx);
   const int fixed = ymode ? (int)strip_index(c, nx, npx) : ys_row(ys, c);
   const int64_t idx = ymode ? (int64_t)fixed + nx * (int64_t)gi : (int64_t)gi + nx * (int64_t)fixed;
-  const T w = corner ? T(0.5) * wl : wl;
-  out[idx] += w * (d0[i] * bi);
+  const cplx<T> upd = d0[i] * bi;
+  if (!corner) { out[idx] += wl * upd; return; }
+  const T w = T(0.5) * wl;
+  if (sizeof(T) != 4 || slots == nullptr) { out[idx] += w * upd; return; }
+  const int nys = (ys.a1 - ys.a0) + (ys.b1 - ys.b0);
+  const int xl = ymode ? c : (int)strip_line(gi, nx, npx);     // strip column number 0 .. 2 npx - 1
+  const int yl = ymode ? ys_line(ys, gi) : c;                  // strip row number 0 .. nys - 1
+  unsigned long long* slot = slots + (size_t)xl * nys + yl;
+  constexpr unsigned long long kEmpty = 0xFFFFFFFFFFFFFFFFull;    // (NaN, NaN) with an all-ones payload: never produced by arithmetic
+  unsigned long long mine = ((unsigned long long)__float_as_uint((float)upd.y) << 32) | (unsigned long long)__float_as_uint((float)upd.x);
+  if (mine == kEmpty) mine = 0x7FC000007FC00000ull;             // keep the sentinel unique (a diverged iterate is NaN anyway)
+  const unsigned long long other = atomicExch(slot, mine);
+  if (other == kEmpty) return;                                  // first to arrive: the partner finishes the update
+  const cplx<T> o(T(__uint_as_float((unsigned)(other & 0xFFFFFFFFull))), T(__uint_as_float((unsigned)(other >> 32))));
+  const cplx<T> yu = ymode ? upd : o, xu = ymode ? o : upd;
+  out[idx] += w * (yu + xu);
+  *slot = kEmpty;
 }
 
 // ---- residual + restriction (coarse-point-centric).  r_c(I,J) = sum RX[I][a] RY[J][b] r(xi[a], yi[b]) with
@@ -1048,6 +1066,10 @@ template <typename T> int Multigrid<T>::setup(fdfd_ctx* ctx_, const FineOp& op, 
       CUDA_TRY(ctx, L.pcr_y.alloc((size_t)2 * L.npx * L.sy.nseg * (2 * L.sy.K + 1) * L.sy.SL));
       scratch_need = std::max(scratch_need, (size_t)2 * L.npx * L.sy.nseg * 6 * L.sy.SL);
     }
+    if (L.npx > 0 && L.ys.count() > 0 && sizeof(T) == 4) {
+      CUDA_TRY(ctx, L.corner_slots.alloc((size_t)2 * L.npx * L.ys.count()));
+      CUDA_TRY(ctx, cudaMemsetAsync(L.corner_slots.p, 0xFF, (size_t)2 * L.npx * L.ys.count() * sizeof(unsigned long long), ctx->stream));
+    }
     if (L.ys.count() > 0) {
       CUDA_TRY(ctx, L.rys.alloc((size_t)L.ys.count() * L.nx));
       CUDA_TRY(ctx, L.pcr_x.alloc((size_t)L.ys.count() * L.sx.nseg * (2 * L.sx.K + 1) * L.sx.SL));
@@ -1106,18 +1128,22 @@ template <typename T> int Multigrid<T>::smooth(int l, bool zero, bool prolong) {
   KLAUNCH(ctx);
   if (!zero) std::swap(L.u.p, L.tmp.p);
   const int nby = 2 * L.npx * L.sy.nseg, nbx = L.ys.count() * L.sx.nseg;
-  if (!(mg_skip() & 1)) {
-    // y-lines first, then x-lines: a corner point is updated by both (see k_lines2), never by two CTAs of one launch
-    if (nby > 0) {
-      const int threads = std::max(32, ((L.sy.SL + 31) / 32) * 32);
-      k_lines2<T><<<nby, threads, (size_t)2 * L.sy.SL * sizeof(cplx<T>), ctx->stream>>>(L.nx, L.ny, L.npx, L.ys, L.sy, L.sx, L.pcr_y.p, L.pcr_x.p,
-                                                                                     L.rxs.p, L.rys.p, L.u.p, wl, 0, done);
+  if (!(mg_skip() & 1) && nby + nbx > 0) {
+    if (L.corner_slots.p || nby == 0 || nbx == 0) {
+      // one launch for all lines (the corner points' two updates meet in L.corner_slots, see k_lines2)
+      const int slmax = std::max(nby > 0 ? L.sy.SL : 0, nbx > 0 ? L.sx.SL : 0);
+      const int threads = std::max(32, ((slmax + 31) / 32) * 32);
+      k_lines2<T><<<nby + nbx, threads, (size_t)2 * slmax * sizeof(cplx<T>), ctx->stream>>>(L.nx, L.ny, L.npx, L.ys, L.sy, L.sx, L.pcr_y.p, L.pcr_x.p,
+                                                                                         L.rxs.p, L.rys.p, L.u.p, wl, 0, L.corner_slots.p, done);
       KLAUNCH(ctx);
-    }
-    if (nbx > 0) {
-      const int threads = std::max(32, ((L.sx.SL + 31) / 32) * 32);
-      k_lines2<T><<<nbx, threads, (size_t)2 * L.sx.SL * sizeof(cplx<T>), ctx->stream>>>(L.nx, L.ny, L.npx, L.ys, L.sy, L.sx, L.pcr_y.p, L.pcr_x.p,
-                                                                                     L.rxs.p, L.rys.p, L.u.p, wl, nby, done);
+    } else {
+      // fp64 multigrid: y-lines first, then x-lines, so that a corner point is never updated by two CTAs of one launch
+      const int ty = std::max(32, ((L.sy.SL + 31) / 32) * 32), tx = std::max(32, ((L.sx.SL + 31) / 32) * 32);
+      k_lines2<T><<<nby, ty, (size_t)2 * L.sy.SL * sizeof(cplx<T>), ctx->stream>>>(L.nx, L.ny, L.npx, L.ys, L.sy, L.sx, L.pcr_y.p, L.pcr_x.p,
+                                                                                L.rxs.p, L.rys.p, L.u.p, wl, 0, nullptr, done);
+      KLAUNCH(ctx);
+      k_lines2<T><<<nbx, tx, (size_t)2 * L.sx.SL * sizeof(cplx<T>), ctx->stream>>>(L.nx, L.ny, L.npx, L.ys, L.sy, L.sx, L.pcr_y.p, L.pcr_x.p,
+                                                                                L.rxs.p, L.rys.p, L.u.p, wl, nby, nullptr, done);
       KLAUNCH(ctx);
     }
   }

@@ -224,7 +224,7 @@ def test_config2_directional_coupler_fullsize(fdfd):
     assert pin > 0 and abs(pout / pin - 1) < 0.05
 
 
-def _oracle_device(d):
+def _oracle_device_of(d):
     g = d.grid
     go = O.Grid2D(O_dh(g), list(g.Npml), [g.bounds[0][0], g.bounds[1][0]], [g.bounds[0][1], g.bounds[1][1]])
     assert go.size() == tuple(g.N)
@@ -251,7 +251,7 @@ def test_bench_map_vs_oracle_direct_solve(fdfd, n, solver):
     kw = {} if solver == "auto" else {"solver": fdfd._lib.SOLVER_MLKRYLOV}
     f = fdfd.solve(d, fdfd.TM, **kw)
     assert f.info["flag"] == 0 and f.info["relres"] <= RES_TOL
-    fo = O.solve(_oracle_device(d), O.TM)
+    fo = O.solve(_oracle_device_of(d), O.TM)
     for c in range(3):   # Ez, Hx, Hy separately: the H components are derivatives of Ez (driven.jl:40-41) and 1e3 smaller
         assert rel(f.data[:, :, c], fo["data"][:, :, c]) <= FIELD_TOL
     assert rel(f.data, fo["data"]) <= FIELD_TOL
@@ -270,7 +270,7 @@ def test_config2_directional_coupler_vs_direct_solve(fdfd):
     d = wl.directional_coupler(fdfd)
     f = fdfd.solve(d)
     assert f.info["flag"] == 0 and f.info["relres"] <= RES_TOL
-    do = _oracle_device(d)
+    do = _oracle_device_of(d)
     do.src[:] = 0                     # the oracle launches its own mode source (driven.jl:15-19), it does not inherit the product's
     m = d.modes[0]
     do.modes.append(O.Mode(O.TM, O.X, m.neff, (m.pt.x, m.pt.y), m.width))
