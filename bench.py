@@ -53,6 +53,7 @@ def parse():
                     help="sweep mode: auto (library default: multilevel Krylov from 2^22 grid points, BiCGSTAB below), or force one")
     ap.add_argument("--ml-spec", default="", help="--solver mlkrylov: FGMRES steps on levels 1,2[,3] (default: library default 6,6)")
     ap.add_argument("--ml-restart", type=int, default=0, help="--solver mlkrylov: level-0 restart length (0: a 1/concurrency share of the free HBM, at most 96)")
+    ap.add_argument("--maxit", type=int, default=0, help="Krylov iteration cap (0: library default 20000)")
     ap.add_argument("--concurrency", type=int, default=0, help="frequencies solved at the same time (default: --sweep)")
     ap.add_argument("--mode", default="sweep", choices=["sweep", "slab"],
                     help="sweep (default, the metric): disjoint frequencies per GPU, weak scaling.  slab: ONE --grid^2 solve split "
@@ -388,6 +389,8 @@ def slab_run(args, n, fdfd, ctx, stream, rank, world, local, steps, warmup, e2e)
     g, omega, eps_rows, src_rows = wl.synthetic_tm_device(fdfd, n, n, density=args.density, rows=(y0, nr))
     gc = g.as_c()
     opts = fdfd.default_opts()
+    if args.maxit > 0:
+        opts.maxit = args.maxit
     M = n * nr
     eps_h = torch.from_numpy(np.asfortranarray(eps_rows).ravel(order="F").copy()).pin_memory()
     src_h = torch.from_numpy(np.asfortranarray(src_rows).ravel(order="F").copy()).pin_memory()
