@@ -334,7 +334,7 @@ def b200_arm(args):
                 "converged": bool(flags.item()),
                 "solve": {"solves_per_step_per_gpu": B, "iters": [i["iters"] for i in infos], "relres_max": max(i["relres"] for i in infos),
                           "krylov_ms": [round(i["solve_ms"], 1) for i in infos], "setup_ms": [round(i["setup_ms"], 1) for i in infos],
-                          "mg_levels": infos[0]["mg_levels"], "per_rank": per_rank},
+                          "restarts": [i["restarts"] for i in infos], "mg_levels": infos[0]["mg_levels"], "per_rank": per_rank},
                 "e2e": {"value": world * B * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": world * 2 * N * 16,
                         "d2h_bytes_per_step": world * B * 3 * N * 16, "steps": e2e_steps, "clocks": clk_e2e.summary(),
                         "call_ms": [round(i["total_ms"], 1) for i in e2e_infos], "krylov_ms": [round(i["solve_ms"], 1) for i in e2e_infos]},
@@ -454,6 +454,7 @@ def slab_run(args, n, fdfd, ctx, stream, rank, world, local, steps, warmup, e2e)
            "converged": bool(ok.item()),
            "solve": {"iters": [i["iters"] for i in infos], "relres": [i["relres"] for i in infos],
                      "krylov_ms": [round(i["solve_ms"], 1) for i in infos], "setup_ms": [round(i["setup_ms"], 1) for i in infos],
+                     "restarts": [i["restarts"] for i in infos],
                      "mg_levels": i0["mg_levels"], "ms_per_iteration": i0["solve_ms"] / max(1, i0["iters"])},
            "e2e": None if not e2e else {"value": 1.0 / t_e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * M * 16 * world,
                                         "d2h_bytes_per_step": 3 * M * 16 * world, "steps": 1},
