@@ -9,6 +9,7 @@ from fdfd_jl_b200 import slab
 
 dh, a, q = 0.01, 0.2202, 2.9263
 w, Om = 2 * math.pi * 1.939e14, 4.541e14
+NS = int(os.environ.get("NSLABS", 4))
 args = [int(v) for v in sys.argv[1:]]
 for Nx, Ny in zip(args[0::2], args[1::2]):
     g = fdfd.Grid(dh, [15, 15], [0.0, Nx * dh], [-Ny * dh / 2, Ny * dh / 2])
@@ -19,8 +20,8 @@ for Nx, Ny in zip(args[0::2], args[1::2]):
     mod = (xs >= 0.1 * Lx) & (xs <= 0.9 * Lx) & (ys >= -a / 2) & (ys <= 0)
     d.deps_r = np.where(mod, np.exp(1j * q * xs) * np.ones((1, Ny)), 0)
     d.src = np.zeros((Nx, Ny), dtype=complex); d.src[25, :] = np.where(np.abs(ys[0]) <= 2 * a, 1j, 0)
-    for tag, run in (("single GPU", lambda: fdfd.solve(d, maxit=6000)[0][1].info),
-                     ("4 slabs (threads)", lambda: slab.solve_modulated_slabs_threads(d, 4, maxit=6000)[1][0])):
+    for tag, run in (("single GPU", lambda: fdfd.solve(d, maxit=int(os.environ.get("MAXIT", 6000)))[0][1].info),
+                     (f"{NS} slabs (threads)", lambda: slab.solve_modulated_slabs_threads(d, NS, maxit=int(os.environ.get("MAXIT", 6000)))[1][0])):
         t0 = time.time()
         try:
             i = run()
