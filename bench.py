@@ -306,6 +306,13 @@ def b200_arm(args):
         ms_k = P.bench_mg(kind, 100)
         mg_kernels.append({"kernel": name, "algorithmic_bytes_per_point": bpp, "ms_per_launch": ms_k, "achieved_gbs": bpp * N / (ms_k * 1e-3) / 1e9})
     ms_cycle = P.bench_mg(4, 50)
+    # the batched stencil: B right-hand sides sharing the operator in ONE launch (the solvers do not use it yet -- see DESIGN.md 7)
+    batched = []
+    for nb in (1, 4, 8):
+        ms_b = P.bench_apply_batched(nb, 60)
+        bytes_b = (32.0 * nb + 16.0) * N
+        batched.append({"nrhs": nb, "ms_per_launch": ms_b, "algorithmic_bytes_per_point_per_rhs": (32.0 * nb + 16.0) / nb,
+                        "achieved_gbs": bytes_b / (ms_b * 1e-3) / 1e9, "us_per_rhs": 1e3 * ms_b / nb})
     P.close()
     peak, peak_src = measured_peak()
     achieved = ALG_BYTES_PER_POINT * N / (ms_apply * 1e-3) / 1e9
@@ -347,7 +354,11 @@ def b200_arm(args):
                 "roofline_multigrid": {"note": "the kernels that take most of a step (k_apply is ~9 % of it); same live CUDA-event timing, same peak",
                                        "peak": peak, "unit": "GB/s",
                                        "kernels": [dict(k, frac=k["achieved_gbs"] / peak) for k in mg_kernels],
-                                       "ms_per_cycle": ms_cycle}}
+                                       "ms_per_cycle": ms_cycle},
+                "roofline_batched": {"kernel": "k_apply_batched (B right-hand sides sharing one operator per launch: (32 B + 16) / B algorithmic B/pt/rhs; "
+                                               "kernel-level measurement, the Krylov solvers take one right-hand side per solve)",
+                                     "peak": peak, "unit": "GB/s", "runs": [dict(b, frac=b["achieved_gbs"] / peak) for b in batched],
+                                     "speedup_per_rhs_B4_vs_single_k_apply": ms_apply / (batched[1]["ms_per_launch"] / 4.0)}}
         if slab_rec is not None:
             line["slab"] = slab_rec
         if not args.no_cpu_baseline and world == 1:

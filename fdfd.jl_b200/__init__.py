@@ -487,6 +487,22 @@ def apply_operator(g: Grid, pol, omega, eps_r, x, ordering=_lib.ORDER_FB, ctx=No
     return y
 
 
+def apply_operator_batched(g: Grid, pol, omega, eps_r, X, ordering=_lib.ORDER_FB, ctx=None):
+    """Y[:, :, b] = A X[:, :, b] for right-hand sides sharing one operator: the stencil reads the coefficients once per point for
+    all of them ((32 B + 16) / B bytes per point and right-hand side instead of 48).  X: (Nx, Ny, B)."""
+    ctx = ctx or default_context()
+    X = np.asarray(X)
+    if X.ndim != 3 or X.shape[:2] != tuple(g.N):
+        raise ValueError("X must have shape (Nx, Ny, B)")
+    B = X.shape[2]
+    eps = as_c128(eps_r, g.N)
+    xx = np.asfortranarray(X, dtype=np.complex128)
+    Y = np.empty(tuple(g.N) + (B,), dtype=np.complex128, order="F")
+    gc = g.as_c()
+    check(lib().fdfd_apply_operator_batched(ctx.handle, C.byref(gc), pol, ordering, omega, ptr(eps), B, ptr(xx), ptr(Y)), ctx.handle)
+    return Y
+
+
 def rasterize(g: Grid, shapes, eps_r=None, ctx=None):
     """setup_ϵᵣ!(d, shapes) on the GPU for Box / Cylinder shapes with constant data (src/device.jl:47-61)."""
     ctx = ctx or default_context()
@@ -544,6 +560,12 @@ class Problem:
     def bench_apply(self, nrep=50):
         ms = C.c_double()
         check(lib().fdfd_problem_bench_apply(self._h, nrep, C.byref(ms)), self.ctx.handle)
+        return ms.value
+
+    def bench_apply_batched(self, nrhs, nrep=50):
+        """ms per launch of the batched stencil: `nrhs` (1, 2, 4 or 8) right-hand sides sharing this problem's operator"""
+        ms = C.c_double()
+        check(lib().fdfd_problem_bench_apply_batched(self._h, int(nrhs), nrep, C.byref(ms)), self.ctx.handle)
         return ms.value
 
     def bench_mg(self, kind, nrep=50):

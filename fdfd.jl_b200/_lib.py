@@ -62,7 +62,7 @@ EXPORTS = [
     "fdfd_problem_create", "fdfd_problem_destroy", "fdfd_problem_set_rhs", "fdfd_problem_set_source",
     "fdfd_problem_solve", "fdfd_problem_get_solution", "fdfd_problem_get_fields", "fdfd_problem_bench_apply", "fdfd_problem_bench_mg",
     "fdfd_problem_precond", "fdfd_problem_get_history", "fdfd_debug_hess_eig",
-    "fdfd_debug_general_eig", "fdfd_debug_krylov_schur",
+    "fdfd_debug_general_eig", "fdfd_debug_krylov_schur", "fdfd_apply_operator_batched", "fdfd_problem_bench_apply_batched",
     "fdfd_problem_flux_x", "fdfd_rasterize",
     "fdfd_comm_unique_id", "fdfd_comm_create_nccl", "fdfd_comm_group_create", "fdfd_comm_group_destroy",
     "fdfd_comm_create_threads", "fdfd_comm_destroy", "fdfd_slab_rows", "fdfd_solve_driven_slab", "fdfd_comm_stats",
@@ -118,6 +118,8 @@ def lib():
         L.fdfd_debug_ml_transfer_gpu.argtypes = [vp, i64, i64, i32, dbl, vp, vp]
         L.fdfd_problem_get_history.argtypes = [vp, vp, i32, C.POINTER(i32)]
         L.fdfd_debug_hess_eig.argtypes = [i32, vp, vp, vp]
+        L.fdfd_apply_operator_batched.argtypes = [vp, G, i32, i32, dbl, vp, i32, vp, vp]
+        L.fdfd_problem_bench_apply_batched.argtypes = [vp, i32, i32, C.POINTER(dbl)]
         L.fdfd_debug_general_eig.argtypes = [i32, vp, vp, vp]
         L.fdfd_debug_krylov_schur.argtypes = [i32, vp, i32, i32, i32, dbl, i32, vp, vp, C.POINTER(i32), C.POINTER(i32)]
         L.fdfd_problem_flux_x.argtypes = [vp, dbl, dbl, dbl, i32, C.POINTER(dbl)]

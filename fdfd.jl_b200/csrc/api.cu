@@ -184,6 +184,30 @@ extern "C" int fdfd_problem_bench_apply(fdfd_problem* P, int nrep, double* ms_pe
   return FDFD_OK;
 }
 
+// ms per launch of the batched stencil (nrhs right-hand sides sharing the problem's operator), timed like fdfd_problem_bench_apply
+extern "C" int fdfd_problem_bench_apply_batched(fdfd_problem* P, int nrhs, int nrep, double* ms_per_launch) {
+  if (!P) return FDFD_ERR_ARG;
+  fdfd_ctx* ctx = P->ctx;
+  ARG_CHECK(ctx, nrep > 0 && ms_per_launch && (nrhs == 1 || nrhs == 2 || nrhs == 4 || nrhs == 8), "bad arguments (nrhs in {1, 2, 4, 8})");
+  const int64_t N = P->op.g.Nx * P->op.g.Ny;
+  const bool te = P->op.pol == FDFD_TE;
+  DevBuf<c128> xa, xb;
+  CUDA_TRY(ctx, xa.alloc((size_t)nrhs * N)); CUDA_TRY(ctx, xb.alloc((size_t)nrhs * N));
+  k_fill_random<<<P->w.nvec_blocks, 256, 0, ctx->stream>>>((int64_t)nrhs * N, xa.p, 99); KLAUNCH(ctx);
+  for (int w = 0; w < 3; ++w) FDFD_TRY(launch_apply_batched(ctx, P->op.view(), te, xa.p, xb.p, nrhs, N));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(ctx, cudaEventCreate(&e0)); CUDA_TRY(ctx, cudaEventCreate(&e1));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
+  for (int i = 0; i < nrep; ++i) FDFD_TRY(launch_apply_batched(ctx, P->op.view(), te, (i & 1) ? xb.p : xa.p, (i & 1) ? xa.p : xb.p, nrhs, N));
+  CUDA_TRY(ctx, cudaEventRecord(e1, ctx->stream));
+  CUDA_TRY(ctx, cudaEventSynchronize(e1));
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *ms_per_launch = (double)ms / nrep;
+  return FDFD_OK;
+}
+
 extern "C" int fdfd_problem_bench_mg(fdfd_problem* P, int kind, int nrep, double* ms_per_launch) {
   if (!P) return FDFD_ERR_ARG;
   fdfd_ctx* ctx = P->ctx;

@@ -67,6 +67,9 @@ struct DotSpec {
 int launch_apply(fdfd_ctx* ctx, const OpView<double>& op, bool te, const void* x, bool x_is_f32, c128* y, const DotSpec& ds,
                  const Coupling* cpl = nullptr);
 
+// y_b = A x_b for nrhs right-hand sides sharing the operator (vectors `stride` elements apart): coefficients read once per point
+int launch_apply_batched(fdfd_ctx* ctx, const OpView<double>& op, bool te, const c128* x, c128* y, int nrhs, int64_t stride);
+
 // H/E recovery written straight into the (Nx,Ny,3) output (K9).  mode: see stencil.cu
 int launch_recover(fdfd_ctx* ctx, const FineOp& op, const c128* u, int forward, std::complex<double> omega_field,
                    int te_swap, c128* fields3);

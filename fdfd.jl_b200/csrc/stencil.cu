@@ -250,6 +250,80 @@ int FineOp::build_level(fdfd_ctx* ctx, const fdfd_grid_t& gfine, int pol_, int64
   return FDFD_OK;
 }
 
+
+// ---- B right-hand sides sharing ONE operator (the batch axis of the reference's sweep, driven.jl:11, restricted to sources that share
+// a frequency): the coefficients -- above all the 16 B/pt of w^2 eps (TM) or the two inverse averaged eps arrays (TE) -- are read once
+// per point and applied to B vectors: (32 B + 16) / B algorithmic bytes per point and right-hand side instead of 48.
+// Same marching scheme and the same arithmetic as k_apply (the compiler contracts the FMAs differently: results agree to rounding).
+template <bool TE, int B, int ROWS>
+__global__ void __launch_bounds__(kApplyThreads, B >= 4 ? 3 : 6)
+k_apply_batched(OpView<double> op, const c128* __restrict__ x, c128* __restrict__ y, int64_t stride) {
+  const int64_t Nx = op.nx, Ny = op.ny;
+  const int64_t ix = blockIdx.x * (int64_t)kApplyThreads + threadIdx.x;
+  const int64_t iy0 = blockIdx.y * (int64_t)ROWS;
+  if (ix >= Nx) return;
+  const int64_t ixm = ix == 0 ? Nx - 1 : ix - 1, ixp = ix + 1 == Nx ? 0 : ix + 1;
+  const c128 cw = op.cxm[ix], ce = op.cxp[ix];
+  const int64_t iym0 = iy0 == 0 ? Ny - 1 : iy0 - 1;
+  c128 us[B], uc[B];
+#pragma unroll
+  for (int b = 0; b < B; ++b) { us[b] = x[b * stride + ix + Nx * iym0]; uc[b] = x[b * stride + ix + Nx * iy0]; }
+  c128 gyc = TE ? op.gy[ix + Nx * iy0] : c128(1.0, 0.0);
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    const int64_t iy = iy0 + r;
+    if (iy >= Ny) break;
+    const int64_t iyp = iy + 1 == Ny ? 0 : iy + 1;
+    const int64_t n = ix + Nx * iy;
+    c128 W = cw, E = ce, S = op.cym[iy], Nn = op.cyp[iy], m;
+    if (TE) {
+      const c128 gyn = op.gy[ix + Nx * iyp];
+      W = W * op.gx[n]; E = E * op.gx[ixp + Nx * iy];
+      S = S * gyc; Nn = Nn * gyn;
+      gyc = gyn;
+      m = op.mass_const;
+    } else {
+      m = ld_stream(op.mass + n);
+    }
+    const c128 C = ((-W - E) + (-S - Nn)) + m;
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+      const c128* xb = x + b * stride;
+      const c128 un = xb[ix + Nx * iyp];
+      const c128 uw = xb[ixm + Nx * iy], ue = xb[ixp + Nx * iy];
+      c128 out = C * uc[b];
+      cfma(out, W, uw); cfma(out, E, ue); cfma(out, S, us[b]); cfma(out, Nn, un);
+      st_stream(y + b * stride + n, out);
+      us[b] = uc[b]; uc[b] = un;
+    }
+  }
+}
+
+template <bool TE, int B>
+static int launch_apply_batched_b(fdfd_ctx* ctx, const OpView<double>& op, const c128* x, c128* y, int64_t stride) {
+  constexpr int ROWS = 4;
+  dim3 grid((unsigned)((op.nx + kApplyThreads - 1) / kApplyThreads), (unsigned)((op.ny + ROWS - 1) / ROWS));
+  k_apply_batched<TE, B, ROWS><<<grid, kApplyThreads, 0, ctx->stream>>>(op, x, y, stride);
+  KLAUNCH(ctx);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return FDFD_OK;
+}
+
+// y_b = A x_b, b < nrhs; vectors stride elements apart.  Any nrhs: chunks of 8 / 4 / 2 / 1.
+int launch_apply_batched(fdfd_ctx* ctx, const OpView<double>& op, bool te, const c128* x, c128* y, int nrhs, int64_t stride) {
+  int done = 0;
+  while (done < nrhs) {
+    const int left = nrhs - done;
+    const int B = left >= 8 ? 8 : left >= 4 ? 4 : left >= 2 ? 2 : 1;
+    const c128* xb = x + (size_t)done * stride; c128* yb = y + (size_t)done * stride;
+#define GO(BV) (te ? launch_apply_batched_b<true, BV>(ctx, op, xb, yb, stride) : launch_apply_batched_b<false, BV>(ctx, op, xb, yb, stride))
+    FDFD_TRY(B == 8 ? GO(8) : B == 4 ? GO(4) : B == 2 ? GO(2) : GO(1));
+#undef GO
+    done += B;
+  }
+  return FDFD_OK;
+}
+
 template <typename TI, bool TE, int NDOT, int ROWS, int MINB, bool HINT>
 static int launch_apply_v(fdfd_ctx* ctx, const OpView<double>& op, const TI* x, c128* y, const DotSpec& ds, const Coupling* cpl) {
   const int64_t row_hi = ds.row_hi < 0 ? op.ny : ds.row_hi;
@@ -357,6 +431,29 @@ extern "C" int fdfd_apply_operator(fdfd_ctx* ctx, const fdfd_grid_t* g, int pol,
   DotSpec ds;
   FDFD_TRY(launch_apply(ctx, op.view(), pol == FDFD_TE, dx.p, false, dy.p, ds));
   FDFD_TRY(fdfd_copy_out(ctx, y, dy.p, N * sizeof(c128)));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return FDFD_OK;
+}
+
+// apply_operator for nrhs right-hand sides that share the operator: x, y are nrhs x (Nx,Ny), column-major, one after the other
+extern "C" int fdfd_apply_operator_batched(fdfd_ctx* ctx, const fdfd_grid_t* g, int pol, int ordering, double omega,
+                                           const fdfd_c128* eps_r, int nrhs, const fdfd_c128* x, fdfd_c128* y) {
+  ARG_CHECK(ctx, ctx != nullptr, "ctx is NULL");
+  FDFD_TRY(check_grid(ctx, g));
+  ARG_CHECK(ctx, pol == FDFD_TM || pol == FDFD_TE, "pol must be FDFD_TM or FDFD_TE");
+  ARG_CHECK(ctx, ordering == FDFD_ORDER_FB || ordering == FDFD_ORDER_BF, "bad ordering");
+  ARG_CHECK(ctx, eps_r && x && y, "NULL argument");
+  ARG_CHECK(ctx, omega > 0, "omega must be > 0");
+  ARG_CHECK(ctx, nrhs >= 1 && nrhs <= 64, "nrhs must be in [1, 64]");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const int64_t N = g->Nx * g->Ny;
+  FineOp op;
+  FDFD_TRY(op.build(ctx, *g, pol, ordering, omega, eps_r));
+  DevBuf<c128> dx, dy;
+  CUDA_TRY(ctx, dx.alloc((size_t)nrhs * N)); CUDA_TRY(ctx, dy.alloc((size_t)nrhs * N));
+  FDFD_TRY(fdfd_copy_in(ctx, dx.p, x, (size_t)nrhs * N * sizeof(c128)));
+  FDFD_TRY(launch_apply_batched(ctx, op.view(), pol == FDFD_TE, dx.p, dy.p, nrhs, N));
+  FDFD_TRY(fdfd_copy_out(ctx, y, dy.p, (size_t)nrhs * N * sizeof(c128)));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return FDFD_OK;
 }

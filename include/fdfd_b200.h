@@ -289,6 +289,15 @@ int fdfd_debug_sell_spmv(int64_t n, const int64_t* colptr, const int64_t* rowval
 
 /* host-only test hook (no GPU needed): the small dense complex Hessenberg eigen-solver behind the Ritz pairs of
  * fdfd_eigenfrequency.  H, evecs: column-major n x n; evals: n. */
+/* y_b = A x_b for nrhs right-hand sides that share ONE operator (sources sharing a frequency -- the batch axis of the reference's sweep
+ * loop, driven.jl:11): the stencil reads the coefficients, above all w^2 eps, once per point for all nrhs vectors:
+ * (32 nrhs + 16) / nrhs algorithmic bytes per point and right-hand side instead of 48.  Equal to nrhs single
+ * fdfd_apply_operator calls to rounding (same arithmetic, different FMA contraction).  x, y: nrhs x (Nx,Ny) one after the other.  Kernel-level building block and benchmark: the Krylov
+ * solvers still take one right-hand side per solve (concurrent streams). */
+int fdfd_apply_operator_batched(fdfd_ctx* ctx, const fdfd_grid_t* g, int pol, int ordering, double omega,
+                                const fdfd_c128* eps_r, int nrhs, const fdfd_c128* x, fdfd_c128* y);
+int fdfd_problem_bench_apply_batched(fdfd_problem* p, int nrhs, int nrep, double* ms_per_launch);
+
 int fdfd_debug_hess_eig(int n, const fdfd_c128* H, fdfd_c128* evals, fdfd_c128* evecs);
 /* host-only test hooks (no GPU needed) of the Krylov-Schur driver behind fdfd_eigenfrequency[_slab] (csrc/arnoldi.cu; stands
  * where Arpack's implicitly restarted Arnoldi stands, eigen.jl:86,104): the eigen-solver of a general small matrix (the projected
