@@ -490,11 +490,11 @@ def apply_operator(g: Grid, pol, omega, eps_r, x, ordering=_lib.ORDER_FB, ctx=No
 def apply_operator_batched(g: Grid, pol, omega, eps_r, X, ordering=_lib.ORDER_FB, ctx=None):
     """Y[:, :, b] = A X[:, :, b] for right-hand sides sharing one operator: the stencil reads the coefficients once per point for
     all of them ((32 B + 16) / B bytes per point and right-hand side instead of 48).  X: (Nx, Ny, B)."""
-    ctx = ctx or default_context()
     X = np.asarray(X)
     if X.ndim != 3 or X.shape[:2] != tuple(g.N):
         raise ValueError("X must have shape (Nx, Ny, B)")
     B = X.shape[2]
+    ctx = ctx or default_context()
     eps = as_c128(eps_r, g.N)
     xx = np.asfortranarray(X, dtype=np.complex128)
     Y = np.empty(tuple(g.N) + (B,), dtype=np.complex128, order="F")

@@ -262,3 +262,20 @@ def test_dolinearsolve_fails_loudly_without_gpu(fdfd):
     assert "no CPU path" in str(e.value)
     with pytest.raises(ValueError):
         fdfd.dolinearsolve(sp.random(3, 4, density=0.5, format="csc"), np.ones(4))
+
+
+def test_batched_apply_host_checks_and_no_cpu_fallback(fdfd):
+    """fdfd_apply_operator_batched: the host mirror checks the (Nx, Ny, B) layout; without a GPU the call fails loudly like every entry point"""
+    import numpy as np
+    import torch
+    g = fdfd.Grid(0.1, [2, 2], [0, 1.0], [0, 0.8])
+    eps = np.ones(g.N, dtype=complex)
+    with pytest.raises(ValueError):
+        fdfd.apply_operator_batched(g, fdfd.TM, 1e15, eps, np.ones(g.N, dtype=complex))          # 2-D: no batch axis
+    with pytest.raises(ValueError):
+        fdfd.apply_operator_batched(g, fdfd.TM, 1e15, eps, np.ones((3, 3, 2), dtype=complex))    # wrong grid
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(fdfd.FdfdError) as e:
+        fdfd.apply_operator_batched(g, fdfd.TM, 1e15, eps, np.ones(g.N + (2,), dtype=complex))
+    assert "no CPU path" in str(e.value)
