@@ -79,7 +79,9 @@ typedef struct {
   double  tol;           /* relative residual ||b-Ax||/||b|| of the un-preconditioned system (default 1e-10) */
   int32_t maxit;         /* Krylov iterations (default 20000) */
   int32_t mg_precision;  /* FDFD_MG_F32 | FDFD_MG_F64 (default F32) */
-  int32_t mg_cycle;      /* FDFD_CYCLE_* (default W, truncated at mg_wdepth) */
+  int32_t mg_cycle;      /* FDFD_CYCLE_* of the BiCGSTAB preconditioner (default W, truncated at mg_wdepth).  The multilevel Krylov solver
+                            always runs F cycles for its M_l^-1 (a W cycle truncated at an absolute depth degenerates to V on its inner
+                            levels; measured 105 against 210 outer iterations at 4096^2) */
   int32_t mg_wdepth;     /* levels [0,wdepth) recurse twice in a W cycle (default 3; measured at 4096^2: 1982 / 1230 / 1263 BiCGSTAB
                             iterations and 6.6 / 5.0 / 6.5 s for depth 2 / 3 / 4) */
   int32_t mg_nu1, mg_nu2;/* pre/post smoothing sweeps (default 1,1) */
@@ -169,7 +171,11 @@ int fdfd_solve_modulated(fdfd_ctx* ctx, const fdfd_grid_t* g, double omega, doub
 /* ---- eigenfrequency.  Replaces eigenfrequency(d, pol, nev; which) (src/solver/eigen.jl:69-115):
  * shift-invert Arnoldi around sigma = -w0^2 mu0 eps0 (TM) / -w0^2 mu0 (TE) with the PML frozen
  * at w0; the inner solves reuse the driven operator.  omega_out: nev complex; fields: nev x (Nx,Ny,3)
- * (may be NULL).  ncv<=0 picks max(20, 2*nev+1) like Arpack.jl. */
+ * (may be NULL).  ncv<=0 picks max(20, 2*nev+1) like Arpack.jl, and like Arpack the basis never holds more than ncv + 1
+ * vectors: Krylov-Schur thick restarts (csrc/arnoldi.cu) keep the nev + (ncv - nev)/2 best Ritz vectors.  A Ritz pair counts as
+ * converged at |b^T y| <= 10 * min(opts->tol, 1e-11) * |nu| (Arpack's machine-epsilon default presumes an exact factorisation
+ * behind the operator; here it is an iterative solve to min(opts->tol, 1e-11)); at most max(300, 30 nev) + ncv operator
+ * applications, then FDFD_ERR_NOCONV.  info->restarts reports the operator applications, info->iters the inner Krylov iterations. */
 int fdfd_eigenfrequency(fdfd_ctx* ctx, const fdfd_grid_t* g, int pol, double omega0, int nev, int which,
                         int ncv, const fdfd_c128* eps_r, const fdfd_solve_opts_t* opts,
                         fdfd_c128* omega_out, fdfd_c128* fields, fdfd_info_t* info);
